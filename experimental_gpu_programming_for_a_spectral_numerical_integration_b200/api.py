@@ -1,0 +1,252 @@
+"""Python host-side mirror of the reference's function surface on top of the C ABI (include/sri.h).
+
+The reference is a single C++ translation unit (main.cpp + two headers); its C++ drop-in lives in
+include/sri_reference_api.hpp.  This module is the same thin layer for Python callers (tests, bench.py, the Newton
+driver): it owns no arithmetic, only pointer plumbing.  Buffers may be torch tensors (CUDA or CPU, float64,
+contiguous) or numpy arrays; device tensors are passed through untouched, host arrays are staged by the library.
+
+Reference names kept (file:line under /root/reference):
+  ComputeChebyshevPoints  include/chebyshev_differentiation.h:19-30
+  GetCoefficients_c       include/chebyshev_differentiation.h:37-52
+  getDn                   include/chebyshev_differentiation.h:59-108
+  Phi                     include/utilities.h:49-67
+  integrateQuaternions    main.cpp:91-118   (the global `qe` becomes an argument)
+  updatePositionb         main.cpp:121-140  (folded into integratePosition on the device)
+  integratePosition       main.cpp:145-176
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+try:  # torch is plumbing (device memory, streams); the library itself does not depend on it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _ptr(x, name: str = "buffer", dtype=np.float64) -> Optional[int]:
+    """Raw address of a contiguous float64 (or int32) buffer; None stays None."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        want = torch.float64 if dtype == np.float64 else torch.int32
+        if x.dtype != want:
+            raise TypeError(f"{name}: expected {want}, got {x.dtype}")
+        if not x.is_contiguous():
+            raise ValueError(f"{name}: tensor must be contiguous")
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        if x.dtype != dtype:
+            raise TypeError(f"{name}: expected {dtype}, got {x.dtype}")
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"{name}: array must be C-contiguous")
+        return x.ctypes.data
+    raise TypeError(f"{name}: expected a torch tensor or numpy array, got {type(x)}")
+
+
+def _empty_like_kind(ref, shape, dtype=np.float64):
+    if _is_torch(ref):
+        return torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, device=ref.device)
+    return np.empty(shape, dtype=dtype)
+
+
+# ---- strain-independent operator ------------------------------------------------------------------------------
+
+def ComputeChebyshevPoints(N: int, L: float = 1.0) -> np.ndarray:
+    x = np.empty(N)
+    _lib.check(_lib.load().sri_chebyshev_points(N, float(L), x.ctypes.data), "sri_chebyshev_points")
+    return x
+
+
+def GetCoefficients_c(N: int) -> np.ndarray:
+    c = np.empty(N)
+    _lib.check(_lib.load().sri_chebyshev_coefficients(N, c.ctypes.data), "sri_chebyshev_coefficients")
+    return c
+
+
+def getDn(N: int) -> np.ndarray:
+    """N x N Chebyshev differentiation matrix on [0,1] (returned as a regular numpy matrix, Dn[i, j])."""
+    buf = np.empty(N * N)
+    _lib.check(_lib.load().sri_chebyshev_dn(N, buf.ctypes.data), "sri_chebyshev_dn")
+    return buf.reshape(N, N).T.copy()  # the C ABI is column-major like Eigen
+
+
+def Phi(na: int, ne: int, X: float, begin: float = 0.0, end: float = 1.0) -> np.ndarray:
+    buf = np.empty(na * na * ne)
+    _lib.check(_lib.load().sri_phi(na, ne, float(X), float(begin), float(end), buf.ctypes.data), "sri_phi")
+    return buf.reshape(na * ne, na).T.copy()
+
+
+# ---- handle -----------------------------------------------------------------------------------------------------
+
+class SpectralRodIntegrator:
+    """Owns an sri_handle: the cached operator set for N nodes on one CUDA device."""
+
+    OPERATORS = {"Dn": 0, "Dn_NN": 1, "Dn_IN": 2, "Dn_NN_inv": 3, "D_TT": 4, "D_TI": 5, "D_TT_inv": 6}
+
+    def __init__(self, N: int = 16, device: int = 0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.sri_create(int(N), int(device), ctypes.byref(self._h)), "sri_create")
+        self.N = int(N)
+        self.M = self.N - 1
+        self.device = int(device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sri_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- plumbing
+    def set_stream(self, stream) -> None:
+        """Enqueue on a torch.cuda.Stream / raw cudaStream_t (None restores the handle's own stream)."""
+        raw = None if stream is None else int(getattr(stream, "cuda_stream", stream))
+        _lib.check(self._lib.sri_set_stream(self._h, raw), "sri_set_stream")
+
+    def use_current_torch_stream(self) -> None:
+        self.set_stream(torch.cuda.current_stream(self.device))
+
+    def synchronize(self) -> None:
+        _lib.check(self._lib.sri_synchronize(self._h), "sri_synchronize")
+
+    def operator(self, name: str) -> np.ndarray:
+        which = self.OPERATORS[name]
+        M, N = self.M, self.N
+        shape = {0: (N, N), 1: (M, M), 2: (M,), 3: (M, M), 4: (M, M), 5: (M,), 6: (M, M)}[which]
+        buf = np.empty(int(np.prod(shape)))
+        _lib.check(self._lib.sri_get_operator(self._h, which, buf.ctypes.data), "sri_get_operator")
+        return buf.reshape(shape[::-1]).T.copy() if len(shape) == 2 else buf
+
+    # -- stages
+    def strain_from_modes(self, qe, out=None):
+        """qe [batch][3*ne] -> K [batch][3][N] (Phi<3,ne>(x_i)*qe, main.cpp:69)."""
+        batch = qe.shape[0]
+        ne = qe.shape[1] // 3
+        K = out if out is not None else _empty_like_kind(qe, (batch, 3, self.N))
+        _lib.check(self._lib.sri_strain_from_modes(self._h, batch, ne, _ptr(qe, "qe"), _ptr(K, "K")), "sri_strain_from_modes")
+        return K
+
+    def integrate_quaternions(self, K, q0=None, out=None, info=None):
+        batch = K.shape[0]
+        Q = out if out is not None else _empty_like_kind(K, (batch, 4, self.M))
+        _lib.check(
+            self._lib.sri_integrate_quaternions(self._h, batch, _ptr(K, "K"), _ptr(q0, "q0"), _ptr(Q, "Q"), _ptr(info, "info", np.int32)),
+            "sri_integrate_quaternions",
+        )
+        return Q
+
+    def integrate_position(self, Q, Gamma=None, r0=None, out=None):
+        batch = Q.shape[0]
+        r = out if out is not None else _empty_like_kind(Q, (batch, 3, self.M))
+        _lib.check(
+            self._lib.sri_integrate_position(self._h, batch, _ptr(Q, "Q"), _ptr(Gamma, "Gamma"), _ptr(r0, "r0"), _ptr(r, "r")),
+            "sri_integrate_position",
+        )
+        return r
+
+    def integrate_stress(self, F_tip, fbar=None, out=None):
+        batch = F_tip.shape[0]
+        n = out if out is not None else _empty_like_kind(F_tip, (batch, 3, self.M))
+        _lib.check(
+            self._lib.sri_integrate_stress(self._h, batch, _ptr(fbar, "fbar"), _ptr(F_tip, "F_tip"), _ptr(n, "n")),
+            "sri_integrate_stress",
+        )
+        return n
+
+    def integrate_couple(self, Q, n, M_tip, q0=None, Gamma=None, lbar=None, out=None):
+        batch = Q.shape[0]
+        m = out if out is not None else _empty_like_kind(Q, (batch, 3, self.M))
+        _lib.check(
+            self._lib.sri_integrate_couple(
+                self._h, batch, _ptr(Q, "Q"), _ptr(q0, "q0"), _ptr(Gamma, "Gamma"), _ptr(n, "n"), _ptr(lbar, "lbar"),
+                _ptr(M_tip, "M_tip"), _ptr(m, "m")),
+            "sri_integrate_couple",
+        )
+        return m
+
+    def integrate_all(self, K, F_tip=None, M_tip=None, q0=None, r0=None, Gamma=None, fbar=None, lbar=None,
+                      Q=None, r=None, n=None, m=None, info=None, want=("Q", "r", "n", "m")):
+        """Fused four-stage integration.  Returns a dict with the requested outputs (allocated if not given)."""
+        batch = K.shape[0]
+        outs = {"Q": Q, "r": r, "n": n, "m": m}
+        shapes = {"Q": (batch, 4, self.M), "r": (batch, 3, self.M), "n": (batch, 3, self.M), "m": (batch, 3, self.M)}
+        for key in want:
+            if outs[key] is None:
+                outs[key] = _empty_like_kind(K, shapes[key])
+        rb = _lib.RodBatch(
+            batch=batch, K=_ptr(K, "K"), q0=_ptr(q0, "q0"), r0=_ptr(r0, "r0"), Gamma=_ptr(Gamma, "Gamma"),
+            fbar=_ptr(fbar, "fbar"), lbar=_ptr(lbar, "lbar"), F_tip=_ptr(F_tip, "F_tip"), M_tip=_ptr(M_tip, "M_tip"),
+            Q=_ptr(outs["Q"], "Q"), r=_ptr(outs["r"], "r"), n=_ptr(outs["n"], "n"), m=_ptr(outs["m"], "m"),
+            info=_ptr(info, "info", np.int32),
+        )
+        _lib.check(self._lib.sri_integrate_all(self._h, ctypes.byref(rb)), "sri_integrate_all")
+        return {k: v for k, v in outs.items() if v is not None}
+
+    def shape_residual(self, K, H_diag, Q, m, M_tip, K0=None, q0=None, rho=None, reduce=None):
+        batch = K.shape[0]
+        H = np.ascontiguousarray(np.asarray(H_diag, dtype=np.float64))
+        if rho is None:
+            rho = _empty_like_kind(K, (batch, 3, self.N))
+        _lib.check(
+            self._lib.sri_shape_residual(
+                self._h, batch, _ptr(K, "K"), _ptr(K0, "K0"), H.ctypes.data, _ptr(Q, "Q"), _ptr(q0, "q0"), _ptr(m, "m"),
+                _ptr(M_tip, "M_tip"), _ptr(rho, "rho"), _ptr(reduce, "reduce")),
+            "sri_shape_residual",
+        )
+        return rho
+
+    def generate_rods(self, seed: int, first_rod: int, batch: int, K=None, F_tip=None, M_tip=None, fbar=None):
+        _lib.check(
+            self._lib.sri_generate_rods(self._h, seed, first_rod, batch, _ptr(K, "K"), _ptr(F_tip, "F_tip"),
+                                        _ptr(M_tip, "M_tip"), _ptr(fbar, "fbar")),
+            "sri_generate_rods",
+        )
+
+    def measure_fp64_peak(self) -> float:
+        v = ctypes.c_double()
+        _lib.check(self._lib.sri_measure_fp64_peak(self._h, ctypes.byref(v)), "sri_measure_fp64_peak")
+        return v.value
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().sri_kernel_launch_count())
+
+
+# ---- the reference's stage functions, single rod, modal strain input (main.cpp:181-205) -----------------------
+
+def integrateQuaternions(qe, N: int = 16, device: int = 0) -> np.ndarray:
+    """Q_stack (4*(N-1),) for one rod with modal strain coordinates qe (9,), as main.cpp:197 prints it."""
+    qe = np.ascontiguousarray(np.asarray(qe, dtype=np.float64).reshape(1, -1))
+    with SpectralRodIntegrator(N, device) as h:
+        K = h.strain_from_modes(qe)
+        return h.integrate_quaternions(K).reshape(-1)
+
+
+def integratePosition(qe, N: int = 16, device: int = 0) -> np.ndarray:
+    """r_stack ((N-1), 3) for one rod, as main.cpp:201 prints it (row i = node i)."""
+    qe = np.ascontiguousarray(np.asarray(qe, dtype=np.float64).reshape(1, -1))
+    with SpectralRodIntegrator(N, device) as h:
+        K = h.strain_from_modes(qe)
+        out = h.integrate_all(K, want=("Q", "r"))
+        return out["r"].reshape(3, N - 1).T.copy()

@@ -1,0 +1,595 @@
+// sri_api.cu -- C ABI (include/sri.h) over the sm_100a kernels.  No torch types, no CPU fallback.
+#include "../../include/sri.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sri_fused16.cuh"
+#include "sri_host_math.hpp"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define SRI_CUDA(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(SRI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+}  // namespace
+
+struct sri_context {
+    int N = 0, M = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int sm_count = 0;
+    sri_host::OperatorSet ops;
+    double* d_ops16 = nullptr;   // OpsLayout16 tables (N <= 16)
+    double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
+    double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
+    int fused_blocks_per_sm = 0;
+    int stage_blocks_per_sm = 0;
+};
+
+namespace {
+
+// ---- device/host buffer staging ----------------------------------------------------------------------------
+
+bool is_device_pointer(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Stages host buffers of one API call through stream-ordered device allocations.
+class Staging {
+public:
+    explicit Staging(sri_context* h) : h_(h) {}
+    ~Staging() {
+        for (void* p : allocs_) cudaFreeAsync(p, h_->stream);
+    }
+    // read-only input: returns a device pointer (nullptr stays nullptr)
+    template <typename T>
+    int in(const T* p, size_t count, const T** out) {
+        *out = nullptr;
+        if (!p || count == 0) return SRI_OK;
+        if (is_device_pointer(p)) { *out = p; return SRI_OK; }
+        void* d = nullptr;
+        SRI_CUDA(cudaMallocAsync(&d, count * sizeof(T), h_->stream));
+        allocs_.push_back(d);
+        SRI_CUDA(cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, h_->stream));
+        *out = static_cast<const T*>(d);
+        used_host_ = true;
+        return SRI_OK;
+    }
+    // output: returns a device pointer; host outputs are copied back by finish()
+    template <typename T>
+    int out(T* p, size_t count, T** outp) {
+        *outp = nullptr;
+        if (!p || count == 0) return SRI_OK;
+        if (is_device_pointer(p)) { *outp = p; return SRI_OK; }
+        void* d = nullptr;
+        SRI_CUDA(cudaMallocAsync(&d, count * sizeof(T), h_->stream));
+        allocs_.push_back(d);
+        backs_.push_back({p, d, count * sizeof(T)});
+        *outp = static_cast<T*>(d);
+        used_host_ = true;
+        return SRI_OK;
+    }
+    int finish() {
+        for (auto& b : backs_) SRI_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, h_->stream));
+        if (used_host_) SRI_CUDA(cudaStreamSynchronize(h_->stream));
+        return SRI_OK;
+    }
+
+private:
+    struct Back { void* host; void* dev; size_t bytes; };
+    sri_context* h_;
+    std::vector<void*> allocs_;
+    std::vector<Back> backs_;
+    bool used_host_ = false;
+};
+
+#define SRI_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != SRI_OK) return rc__; \
+    } while (0)
+
+// ---- small kernels ---------------------------------------------------------------------------------------------
+
+// K[b][c][i] = sum_k P_k(t_i) qe[b][c*ne+k]   (Phi<3,ne>(x_i)*qe, main.cpp:69; Legendre recurrence of utilities.h:59)
+__global__ void strain_from_modes_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
+                                         const double* __restrict__ qe, double* __restrict__ K) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = batch * 3 * N;
+    if (idx >= total) return;
+    const int i = (int)(idx % N);
+    const long long bc = idx / N;  // b*3 + c
+    const double t = tnodes[i];
+    const double* q = qe + bc * ne;
+    double pm = 1.0, p = t, acc = q[0];
+    if (ne > 1) acc = fma(p, q[1], acc);
+    for (int k = 1; k + 1 < ne; ++k) {
+        const double pn = ((2 * k + 1) * t * p - k * pm) / (k + 1);
+        pm = p;
+        p = pn;
+        acc = fma(p, q[k + 1], acc);
+    }
+    K[idx] = acc;
+}
+
+// rho = H (K - K0) - R(q)^T m at all N nodes; block-reduced sum(rho^2) and max|rho| via atomics.
+__global__ void shape_residual_kernel(long long batch, int N, const double* __restrict__ K,
+                                      const double* __restrict__ K0, double h0, double h1, double h2,
+                                      const double* __restrict__ Q, const double* __restrict__ q0,
+                                      const double* __restrict__ m, const double* __restrict__ M_tip,
+                                      double* __restrict__ rho, double* __restrict__ red) {
+    const int M = N - 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s2 = 0.0, mx = 0.0;
+    if (idx < batch * N) {
+        const long long b = idx / N;
+        const int i = (int)(idx % N);
+        sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+        if (i < M) {
+            const double* s = Q + b * 4 * M + i;
+            q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M];
+        } else if (q0) {
+            const double* s = q0 + b * 4;
+            q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3];
+        }
+        double m0, m1, m2;
+        if (i == 0) { const double* s = M_tip + b * 3; m0 = s[0]; m1 = s[1]; m2 = s[2]; }
+        else { const double* s = m + b * 3 * M + (i - 1); m0 = s[0]; m1 = s[M]; m2 = s[2 * M]; }
+        double t0, t1, t2;
+        sri::q_rotate_T(q, m0, m1, m2, t0, t1, t2);
+        const double* k = K + b * 3 * N + i;
+        double k0 = k[0], k1 = k[N], k2 = k[2 * N];
+        if (K0) { const double* z = K0 + b * 3 * N + i; k0 -= z[0]; k1 -= z[N]; k2 -= z[2 * N]; }
+        const double r0 = h0 * k0 - t0, r1 = h1 * k1 - t1, r2 = h2 * k2 - t2;
+        if (rho) { double* d = rho + b * 3 * N + i; d[0] = r0; d[N] = r1; d[2 * N] = r2; }
+        s2 = r0 * r0 + r1 * r1 + r2 * r2;
+        mx = fmax(fabs(r0), fmax(fabs(r1), fabs(r2)));
+    }
+    if (red) {
+        for (int off = 16; off >= 1; off >>= 1) {
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        }
+        __shared__ double sh_s[32], sh_m[32];
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) { sh_s[w] = s2; sh_m[w] = mx; }
+        __syncthreads();
+        if (w == 0) {
+            const int nw = blockDim.x >> 5;
+            s2 = l < nw ? sh_s[l] : 0.0;
+            mx = l < nw ? sh_m[l] : 0.0;
+            for (int off = 16; off >= 1; off >>= 1) {
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            }
+            if (l == 0) {
+                atomicAdd(&red[0], s2);
+                // max of non-negative doubles == max of their bit patterns as unsigned integers
+                atomicMax(reinterpret_cast<unsigned long long*>(&red[1]), (unsigned long long)__double_as_longlong(mx));
+            }
+        }
+    }
+}
+
+// SURVEY 8(d) synthetic rods.  One thread per rod.
+__global__ void generate_rods_kernel(unsigned long long seed, long long first_rod, long long batch, int N,
+                                     const double* __restrict__ tnodes, double* __restrict__ K,
+                                     double* __restrict__ F_tip, double* __restrict__ M_tip,
+                                     double* __restrict__ fbar) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const unsigned long long rod = (unsigned long long)(first_rod + b);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t c0 = (uint32_t)rod, c1 = (uint32_t)(rod >> 32);
+    uint32_t w[4];
+    double u[14];
+    for (int s = 0; s < 7; ++s) {
+        sri::philox4x32_10(c0, c1, (uint32_t)s, 0u, k0, k1, w);
+        u[2 * s] = sri::u01_from_bits(w[0], w[1]);
+        u[2 * s + 1] = sri::u01_from_bits(w[2], w[3]);
+    }
+    if (K) {
+        for (int c = 0; c < 3; ++c) {
+            const double alpha = 4.0 * u[2 * c] - 2.0, beta = 4.0 * u[2 * c + 1] - 2.0;
+            for (int i = 0; i < N; ++i) K[(b * 3 + c) * N + i] = fma(beta, tnodes[i], alpha);
+        }
+    }
+    if (F_tip) for (int c = 0; c < 3; ++c) F_tip[b * 3 + c] = 2.0 * u[6 + c] - 1.0;
+    if (M_tip) for (int c = 0; c < 3; ++c) M_tip[b * 3 + c] = 2.0 * u[9 + c] - 1.0;
+    if (fbar) {
+        const double gload = u[12];
+        for (int i = 0; i < N; ++i) {
+            fbar[(b * 3 + 0) * N + i] = 0.0;
+            fbar[(b * 3 + 1) * N + i] = 0.0;
+            fbar[(b * 3 + 2) * N + i] = -gload;
+        }
+    }
+}
+
+// FP64 FMA peak probe: 16 independent dependent-chains per thread.
+__global__ void fp64_peak_kernel(double* out, int iters, double s) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-9 + i;
+    const double b = s, c = 1.0 - s;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], b, c);
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r += a[i];
+    if (r == 123.456) out[0] = r;
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------------------
+
+constexpr int kFusedThreads = 128;
+constexpr size_t kFusedSmem = (sri::OpsLayout16::total + (kFusedThreads / 32) * sri::kWarpScratch16) * sizeof(double);
+
+template <bool SOLVE>
+int launch_fused16(sri_context* h, const sri::FusedParams& p) {
+    if (p.batch <= 0) return SRI_OK;
+    const long long pairs = (p.batch + 1) / 2;
+    const long long want = (pairs + (kFusedThreads / 32) - 1) / (kFusedThreads / 32);
+    const int per_sm = SOLVE ? h->fused_blocks_per_sm : h->stage_blocks_per_sm;
+    const long long cap = (long long)h->sm_count * per_sm;
+    const int grid = (int)(want < cap ? want : cap);
+    if (h->M == 15)
+        sri::fused16_kernel<15, SOLVE><<<grid, kFusedThreads, kFusedSmem, h->stream>>>(p);
+    else
+        sri::fused16_kernel<0, SOLVE><<<grid, kFusedThreads, kFusedSmem, h->stream>>>(p);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+int check_handle(sri_handle h) {
+    if (!h) return fail(SRI_ERR_INVALID_ARGUMENT, "null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(SRI_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return SRI_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+//  C ABI
+// =================================================================================================================
+
+extern "C" {
+
+const char* sri_last_error_string(void) { return g_last_error.c_str(); }
+int64_t sri_kernel_launch_count(void) { return g_launches.load(); }
+
+int sri_chebyshev_points(int N, double L, double* x) {
+    if (N < 2 || !x) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_chebyshev_points: need N >= 2 and x != NULL");
+    sri_host::chebyshev_points(N, L, x);
+    return SRI_OK;
+}
+
+int sri_chebyshev_coefficients(int N, double* c) {
+    if (N < 2 || !c) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_chebyshev_coefficients: need N >= 2 and c != NULL");
+    sri_host::chebyshev_coefficients(N, c);
+    return SRI_OK;
+}
+
+int sri_chebyshev_dn(int N, double* Dn) {
+    if (N < 2 || !Dn) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_chebyshev_dn: need N >= 2 and Dn != NULL");
+    sri_host::chebyshev_dn(N, Dn);
+    return SRI_OK;
+}
+
+int sri_phi(int na, int ne, double X, double begin, double end, double* out) {
+    if (na < 1 || ne < 1 || !out || end == begin) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_phi: bad arguments");
+    const double x = (2 * X - (end + begin)) / (end - begin);
+    const int cols = na * ne;
+    std::memset(out, 0, sizeof(double) * na * cols);
+    for (int k = 0; k < ne; ++k) {
+        const double pk = sri_host::legendre(k, x);
+        for (int a = 0; a < na; ++a) out[(a * ne + k) * na + a] = pk;
+    }
+    return SRI_OK;
+}
+
+int sri_create(int N, int device, sri_handle* out) {
+    if (!out) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create: out == NULL");
+    *out = nullptr;
+    if (N < 2 || N > 64) return fail(SRI_ERR_UNSUPPORTED_N, "sri_create: N must be in [2, 64]");
+    if (N > 16) return fail(SRI_ERR_UNSUPPORTED_N, "sri_create: N > 16 not built yet in this revision");
+    int ndev = 0;
+    SRI_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SRI_ERR_CUDA, "sri_create: no such CUDA device (there is no CPU fallback)");
+    SRI_CUDA(cudaSetDevice(device));
+    sri_context* h = new (std::nothrow) sri_context();
+    if (!h) return fail(SRI_ERR_ALLOC, "sri_create: out of host memory");
+    h->N = N; h->M = N - 1; h->device = device;
+    if (!h->ops.build(N)) { delete h; return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create: singular differentiation block"); }
+    cudaDeviceProp prop;
+    SRI_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    SRI_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+
+    const int M = h->M;
+    {
+        using L = sri::OpsLayout16;
+        std::vector<double> t(L::total, 0.0);
+        for (int j = 0; j < M; ++j)
+            for (int i = 0; i < M; ++i) {
+                t[L::St + j * sri::MP16 + i] = h->ops.S[j * M + i];
+                t[L::STt + j * sri::MP16 + i] = h->ops.ST[j * M + i];
+            }
+        for (int i = 0; i < M; ++i) {
+            t[L::g + i] = h->ops.g[i];
+            t[L::gT + i] = h->ops.gT[i];
+            t[L::DTI + i] = h->ops.D_TI[i];
+            t[L::DnIN + i] = h->ops.Dn_IN[i];
+        }
+        SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * L::total));
+        SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * L::total, cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<double> t(N);
+        for (int i = 0; i < N; ++i) t[i] = 2 * h->ops.x[i] - 1;
+        SRI_CUDA(cudaMalloc(&h->d_tnodes, sizeof(double) * N));
+        SRI_CUDA(cudaMemcpy(h->d_tnodes, t.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+    }
+    SRI_CUDA(cudaMalloc(&h->d_reduce, sizeof(double) * 2));
+    if (M == 15) {
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_blocks_per_sm, sri::fused16_kernel<15, true>, kFusedThreads, kFusedSmem));
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->stage_blocks_per_sm, sri::fused16_kernel<15, false>, kFusedThreads, kFusedSmem));
+    } else {
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_blocks_per_sm, sri::fused16_kernel<0, true>, kFusedThreads, kFusedSmem));
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->stage_blocks_per_sm, sri::fused16_kernel<0, false>, kFusedThreads, kFusedSmem));
+    }
+    if (h->fused_blocks_per_sm < 1 || h->stage_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: kernel does not fit on this device"); }
+    *out = h;
+    return SRI_OK;
+}
+
+int sri_destroy(sri_handle h) {
+    if (!h) return SRI_OK;
+    cudaSetDevice(h->device);
+    if (h->d_ops16) cudaFree(h->d_ops16);
+    if (h->d_tnodes) cudaFree(h->d_tnodes);
+    if (h->d_reduce) cudaFree(h->d_reduce);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return SRI_OK;
+}
+
+int sri_set_stream(sri_handle h, void* cuda_stream) {
+    SRI_TRY(check_handle(h));
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return SRI_OK;
+}
+
+int sri_synchronize(sri_handle h) {
+    SRI_TRY(check_handle(h));
+    SRI_CUDA(cudaStreamSynchronize(h->stream));
+    return SRI_OK;
+}
+
+int sri_get_N(sri_handle h, int* N) {
+    if (!h || !N) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_N: null argument");
+    *N = h->N;
+    return SRI_OK;
+}
+
+int sri_get_operator(sri_handle h, int which, double* out) {
+    if (!h || !out) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_operator: null argument");
+    const std::vector<double>* src = nullptr;
+    switch (which) {
+        case 0: src = &h->ops.Dn; break;
+        case 1: src = &h->ops.Dn_NN; break;
+        case 2: src = &h->ops.Dn_IN; break;
+        case 3: src = &h->ops.S; break;
+        case 4: src = &h->ops.D_TT; break;
+        case 5: src = &h->ops.D_TI; break;
+        case 6: src = &h->ops.ST; break;
+        default: return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_operator: which must be 0..6");
+    }
+    std::memcpy(out, src->data(), sizeof(double) * src->size());
+    return SRI_OK;
+}
+
+int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe, double* K) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || ne < 1 || (batch > 0 && (!qe || !K))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_strain_from_modes: bad arguments");
+    if (batch == 0) return SRI_OK;
+    Staging st(h);
+    const double* dqe; double* dK;
+    SRI_TRY(st.in(qe, (size_t)batch * 3 * ne, &dqe));
+    SRI_TRY(st.out(K, (size_t)batch * 3 * h->N, &dK));
+    const long long total = (long long)batch * 3 * h->N;
+    strain_from_modes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, dqe, dK);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_integrate_all(sri_handle h, const sri_rod_batch* rods) {
+    SRI_TRY(check_handle(h));
+    if (!rods) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: rods == NULL");
+    const int64_t B = rods->batch;
+    if (B < 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: negative batch");
+    if (B == 0) return SRI_OK;
+    if (!rods->K) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: K is required");
+    if ((rods->n || rods->m) && !rods->F_tip) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: F_tip is required for n/m");
+    if (rods->m && !rods->M_tip) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: M_tip is required for m");
+    const int N = h->N, M = h->M;
+    Staging st(h);
+    sri::FusedParams p{};
+    p.batch = B; p.N = N; p.M = M; p.ops = h->d_ops16;
+    SRI_TRY(st.in(rods->K, (size_t)B * 3 * N, &p.K));
+    SRI_TRY(st.in(rods->q0, (size_t)B * 4, &p.q0));
+    SRI_TRY(st.in(rods->r0, (size_t)B * 3, &p.r0));
+    SRI_TRY(st.in(rods->Gamma, (size_t)B * 3 * N, &p.Gamma));
+    SRI_TRY(st.in(rods->fbar, (size_t)B * 3 * N, &p.fbar));
+    SRI_TRY(st.in(rods->lbar, (size_t)B * 3 * N, &p.lbar));
+    SRI_TRY(st.in(rods->F_tip, (size_t)B * 3, &p.F_tip));
+    SRI_TRY(st.in(rods->M_tip, (size_t)B * 3, &p.M_tip));
+    SRI_TRY(st.out(rods->Q, (size_t)B * 4 * M, &p.Q));
+    SRI_TRY(st.out(rods->r, (size_t)B * 3 * M, &p.r));
+    SRI_TRY(st.out(rods->n, (size_t)B * 3 * M, &p.n));
+    SRI_TRY(st.out(rods->m, (size_t)B * 3 * M, &p.m));
+    SRI_TRY(st.out(rods->info, (size_t)B, &p.info));
+    SRI_TRY(launch_fused16<true>(h, p));
+    return st.finish();
+}
+
+int sri_integrate_quaternions(sri_handle h, int64_t batch, const double* K, const double* q0, double* Q, int* info) {
+    if (batch > 0 && !Q) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_quaternions: Q == NULL");
+    sri_rod_batch rb{};
+    rb.batch = batch; rb.K = K; rb.q0 = q0; rb.Q = Q; rb.info = info;
+    return sri_integrate_all(h, &rb);
+}
+
+int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const double* Gamma, const double* r0, double* r) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || (batch > 0 && (!Q || !r))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_position: bad arguments");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    Staging st(h);
+    sri::FusedParams p{};
+    p.batch = batch; p.N = N; p.M = M; p.ops = h->d_ops16;
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &p.Qin));
+    SRI_TRY(st.in(Gamma, (size_t)batch * 3 * N, &p.Gamma));
+    SRI_TRY(st.in(r0, (size_t)batch * 3, &p.r0));
+    SRI_TRY(st.out(r, (size_t)batch * 3 * M, &p.r));
+    SRI_TRY(launch_fused16<false>(h, p));
+    return st.finish();
+}
+
+int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const double* F_tip, double* n) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || (batch > 0 && (!F_tip || !n))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_stress: bad arguments");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    Staging st(h);
+    sri::FusedParams p{};
+    p.batch = batch; p.N = N; p.M = M; p.ops = h->d_ops16;
+    SRI_TRY(st.in(fbar, (size_t)batch * 3 * N, &p.fbar));
+    SRI_TRY(st.in(F_tip, (size_t)batch * 3, &p.F_tip));
+    SRI_TRY(st.out(n, (size_t)batch * 3 * M, &p.n));
+    SRI_TRY(launch_fused16<false>(h, p));
+    return st.finish();
+}
+
+int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* Gamma,
+                         const double* n, const double* lbar, const double* M_tip, double* m) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || (batch > 0 && (!Q || !n || !M_tip || !m))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_couple: bad arguments");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    Staging st(h);
+    sri::FusedParams p{};
+    p.batch = batch; p.N = N; p.M = M; p.ops = h->d_ops16;
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &p.Qin));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &p.q0));
+    SRI_TRY(st.in(Gamma, (size_t)batch * 3 * N, &p.Gamma));
+    SRI_TRY(st.in(n, (size_t)batch * 3 * M, &p.nin));
+    SRI_TRY(st.in(lbar, (size_t)batch * 3 * N, &p.lbar));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
+    p.F_tip = p.M_tip;  // unused when nin is given; keeps the pointer valid
+    SRI_TRY(st.out(m, (size_t)batch * 3 * M, &p.m));
+    SRI_TRY(launch_fused16<false>(h, p));
+    return st.finish();
+}
+
+int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const double* K0, const double* H_diag,
+                       const double* Q, const double* q0, const double* m, const double* M_tip, double* rho,
+                       double* norm2_and_max) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || (batch > 0 && (!K || !H_diag || !Q || !m || !M_tip))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_shape_residual: bad arguments");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    double H[3];
+    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
+    else std::memcpy(H, H_diag, sizeof(H));
+    Staging st(h);
+    const double *dK, *dK0, *dQ, *dq0, *dm, *dMt; double* drho; double* dred = nullptr;
+    SRI_TRY(st.in(K, (size_t)batch * 3 * N, &dK));
+    SRI_TRY(st.in(K0, (size_t)batch * 3 * N, &dK0));
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &dq0));
+    SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
+    SRI_TRY(st.out(rho, (size_t)batch * 3 * N, &drho));
+    if (norm2_and_max) {
+        SRI_TRY(st.out(norm2_and_max, 2, &dred));
+        SRI_CUDA(cudaMemsetAsync(dred, 0, 2 * sizeof(double), h->stream));
+    }
+    const long long total = (long long)batch * N;
+    shape_residual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, N, dK, dK0, H[0], H[1], H[2], dQ, dq0, dm, dMt, drho, dred);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t batch, double* K, double* F_tip,
+                      double* M_tip, double* fbar) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || first_rod < 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_generate_rods: bad arguments");
+    if (batch == 0) return SRI_OK;
+    for (const void* p : {(const void*)K, (const void*)F_tip, (const void*)M_tip, (const void*)fbar})
+        if (p && !is_device_pointer(p)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_generate_rods: device pointers only");
+    generate_rods_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(seed, first_rod, batch, h->N, h->d_tnodes, K, F_tip, M_tip, fbar);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+int sri_measure_fp64_peak(sri_handle h, double* tflops) {
+    SRI_TRY(check_handle(h));
+    if (!tflops) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_measure_fp64_peak: null argument");
+    double* d = nullptr;
+    SRI_CUDA(cudaMalloc(&d, 8));
+    const int iters = 8192, threads = 512, blocks = h->sm_count * 2;
+    cudaEvent_t e0, e1;
+    SRI_CUDA(cudaEventCreate(&e0));
+    SRI_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        SRI_CUDA(cudaEventRecord(e0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters, 0.5);
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaEventRecord(e1, h->stream));
+        SRI_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SRI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = 2.0 * 16 * iters * (double)blocks * threads / (best * 1e-3) * 1e-12;
+    return SRI_OK;
+}
+
+}  // extern "C"

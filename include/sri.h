@@ -1,0 +1,156 @@
+/*
+ * sri.h -- C ABI of libsri_cuda.so: batched Chebyshev-collocation spectral integration of Cosserat-rod
+ * kinematics and statics on NVIDIA B200 (sm_100a), FP64.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * aGotelli/experimental_gpu_programming_for_a_spectral_numerical_integration.  The reference has no FFI layer:
+ * its "API" is the set of free functions compiled into main.cpp.  Each entry point below names the reference
+ * function (file:line under /root/reference) it replaces.  include/sri_reference_api.hpp keeps the reference's
+ * C++ function names on top of these symbols; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions (identical to the reference so that a single-rod call is byte-compatible with Q_stack/r_stack):
+ *   - N Chebyshev nodes, M = N-1.  Node 0 is the rod tip (X=1), node N-1 the base (X=0)
+ *     (include/chebyshev_differentiation.h:26).
+ *   - per-rod stacks are component-major, node-minor: Q[c*M+i] (main.cpp:80-81,130-133), r[c*M+i] (Eigen
+ *     column-major (N-1)x3, main.cpp:172).  Batches are rod-major and contiguous: rod b's Q starts at Q + b*4*M.
+ *   - stage 1/2 outputs cover nodes 0..N-2 (the base node carries the boundary condition, main.cpp:94-95);
+ *     stage 3/4 outputs cover nodes 1..N-1 (the tip node carries the boundary condition).
+ *   - nodal inputs K, Gamma, fbar, lbar are [batch][3][N] (component-major, node-minor, all N nodes).
+ *   - every data pointer may be a host pointer or a device pointer on the handle's device (detected with
+ *     cudaPointerGetAttributes); host buffers are staged through the handle's device workspace.
+ *   - all functions return SRI_OK (0) or a negative sri_status; nothing throws across this boundary.
+ *     There is no CPU fallback: without a usable CUDA device sri_create fails with SRI_ERR_CUDA.
+ */
+#ifndef SRI_H
+#define SRI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRI_VERSION_MAJOR 0
+#define SRI_VERSION_MINOR 1
+
+typedef enum sri_status {
+    SRI_OK = 0,
+    SRI_ERR_INVALID_ARGUMENT = -1,
+    SRI_ERR_UNSUPPORTED_N = -2,
+    SRI_ERR_CUDA = -3,
+    SRI_ERR_ALLOC = -4,
+    SRI_ERR_SINGULAR = -5 /* at least one rod hit a zero pivot; see the info array */
+} sri_status;
+
+typedef struct sri_context* sri_handle;
+
+/* ---- strain-independent spectral operator (host side, FP64, reference formula order) ------------------- */
+
+/* ComputeChebyshevPoints<N,L>()  include/chebyshev_differentiation.h:19-30.  x[N], descending from L to 0. */
+int sri_chebyshev_points(int N, double L, double* x);
+/* GetCoefficients_c<N>()         include/chebyshev_differentiation.h:37-52.  c[N]. */
+int sri_chebyshev_coefficients(int N, double* c);
+/* getDn<N>()                     include/chebyshev_differentiation.h:59-108. Dn[N*N], column-major. */
+int sri_chebyshev_dn(int N, double* Dn_colmajor);
+/* Phi<na,ne>(X, begin, end)      include/utilities.h:49-67.  out[na * na*ne], column-major na x (na*ne). */
+int sri_phi(int na, int ne, double X, double begin, double end, double* out_colmajor);
+
+/* ---- handle ------------------------------------------------------------------------------------------- */
+
+/* Builds the operator set for N nodes once (replaces the getDn/Kronecker/inverse rebuilds at main.cpp:93-100,
+ * 157-160) and uploads it to `device`.  2 <= N <= 64. */
+int sri_create(int N, int device, sri_handle* out);
+int sri_destroy(sri_handle h);
+/* Work is enqueued on this CUDA stream (a cudaStream_t passed as void*); default: a stream owned by the handle.
+ * Calls with host buffers synchronise the stream before returning; calls with device buffers do not. */
+int sri_set_stream(sri_handle h, void* cuda_stream);
+int sri_synchronize(sri_handle h);
+int sri_get_N(sri_handle h, int* N);
+/* Copies one cached operator to a host buffer.  which: 0 Dn (N*N), 1 Dn_NN (M*M), 2 Dn_IN (M),
+ * 3 Dn_NN^-1 (M*M), 4 D_TT (M*M), 5 D_TI (M), 6 D_TT^-1 (M*M); matrices column-major. */
+int sri_get_operator(sri_handle h, int which, double* out);
+
+/* ---- modal strain adapter ----------------------------------------------------------------------------- */
+
+/* K = Phi<3,ne>(x_i) * qe at every node (main.cpp:69).  qe [batch][3*ne] -> K [batch][3][N]. */
+int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe, double* K);
+
+/* ---- the four integration stages ---------------------------------------------------------------------- */
+
+/* integrateQuaternions()  main.cpp:91-118 with updateA main.cpp:55-88.
+ * Solves ((I4 (x) Dn_NN) - 1/2 blockdiag A(K_i)) Q = -D_IN q0 per rod.
+ * K [batch][3][N]; q0 [batch][4] (w,x,y,z) or NULL => (1,0,0,0) (main.cpp:106-107); Q [batch][4][M];
+ * info [batch] or NULL: 0 ok, k>0 = zero pivot met at elimination step k (the reference would return inf/NaN). */
+int sri_integrate_quaternions(sri_handle h, int64_t batch, const double* K, const double* q0, double* Q,
+                              int* info);
+
+/* integratePosition()  main.cpp:145-176 with updatePositionb main.cpp:121-140, minus the redundant second
+ * quaternion solve (main.cpp:147): r = Dn_NN^-1 (R(q) Gamma - Dn_IN r0^T).
+ * Q [batch][4][M]; Gamma [batch][3][N] or NULL => (1,0,0) (main.cpp:136); r0 [batch][3] or NULL => 0
+ * (main.cpp:151-154); r [batch][3][M]. */
+int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const double* Gamma, const double* r0,
+                           double* r);
+
+/* Internal force n' = -fbar, n(1) = F_tip.  Not implemented by the reference; spec: materials/rod_modeling.pdf
+ * eq. 1.17 with the BC elimination of main.cpp:94-113 mirrored to the tip node.
+ * fbar [batch][3][N] or NULL => 0; F_tip [batch][3]; n [batch][3][M] (nodes 1..N-1). */
+int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const double* F_tip, double* n);
+
+/* Internal couple m' = -(r' x n + lbar), m(1) = M_tip, r' = R(q) Gamma.  Spec: rod_modeling.pdf eq. 1.18;
+ * cross-product convention of skew() include/utilities.h:16-24.
+ * Q [batch][4][M]; q0 as above (rotation of the base node); n [batch][3][M] from sri_integrate_stress;
+ * lbar [batch][3][N] or NULL => 0; M_tip [batch][3]; m [batch][3][M] (nodes 1..N-1). */
+int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* Gamma,
+                         const double* n, const double* lbar, const double* M_tip, double* m);
+
+/* All four stages in one fused launch (what main() does at main.cpp:197-201, plus stages 3-4).  Q never
+ * leaves the SM between stages.  Any of the outputs Q, r, n, m may be NULL to skip storing it; F_tip and
+ * M_tip may be NULL only when both n and m are NULL. */
+typedef struct sri_rod_batch {
+    int64_t batch;
+    const double* K;     /* [batch][3][N]  required */
+    const double* q0;    /* [batch][4]     or NULL  */
+    const double* r0;    /* [batch][3]     or NULL  */
+    const double* Gamma; /* [batch][3][N]  or NULL  */
+    const double* fbar;  /* [batch][3][N]  or NULL  */
+    const double* lbar;  /* [batch][3][N]  or NULL  */
+    const double* F_tip; /* [batch][3] */
+    const double* M_tip; /* [batch][3] */
+    double* Q;           /* [batch][4][M] */
+    double* r;           /* [batch][3][M] */
+    double* n;           /* [batch][3][M] */
+    double* m;           /* [batch][3][M] */
+    int* info;           /* [batch] or NULL */
+} sri_rod_batch;
+int sri_integrate_all(sri_handle h, const sri_rod_batch* rods);
+
+/* ---- static shape problem (rod_modeling.pdf eq. 1.25) ------------------------------------- */
+
+/* rho_i = H (K_i - K0_i) - R(q_i)^T m_i at all N nodes (m_0 = M_tip, q_{N-1} = q0); H = diag(H_diag[3]).
+ * K, K0 (or NULL => 0), rho: [batch][3][N].  Also accumulates sum(rho^2) and max|rho| over the batch into
+ * norm2_and_max[2] (device or host pointer, may be NULL). */
+int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const double* K0, const double* H_diag,
+                       const double* Q, const double* q0, const double* m, const double* M_tip, double* rho,
+                       double* norm2_and_max);
+
+/* ---- synthetic inputs of SURVEY 8(d): counter-based, identical for any sharding ------------------------ */
+
+/* Fills K, F_tip, M_tip, fbar for rods [first_rod, first_rod+batch): K_c(X) = alpha + beta (2X-1) with
+ * alpha,beta ~ U(-2,2); F_tip,M_tip ~ U(-1,1)^3; fbar = (0,0,-g), g ~ U(0,1).  Philox4x32-10 keyed by seed,
+ * counter = rod index.  Any output pointer may be NULL.  Device pointers only. */
+int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t batch, double* K, double* F_tip,
+                      double* M_tip, double* fbar);
+
+/* ---- diagnostics -------------------------------------------------------------------------------------- */
+
+const char* sri_last_error_string(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t sri_kernel_launch_count(void);
+/* Runs the library's FP64 FMA peak probe on the handle's device and returns TFLOP/s (roofline denominator). */
+int sri_measure_fp64_peak(sri_handle h, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRI_H */

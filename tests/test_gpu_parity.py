@@ -1,0 +1,171 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerance: BASELINE.json north_star demands relative error <= 1e-12 per stage in FP64; TOL below is that bound.
+"""
+import numpy as np
+import pytest
+
+from conftest import DEFAULT_QE, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def h16(sri_lib):
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    h = SpectralRodIntegrator(16, 0)
+    yield h
+    h.close()
+
+
+def _gpu_all(h, torch, K, F, Mt, **kw):
+    dev = f"cuda:{h.device}"
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    info = torch.full((K.shape[0],), -1, dtype=torch.int32, device=dev)
+    out = h.integrate_all(t(K), t(F), t(Mt), info=info, **{k: t(v) for k, v in kw.items()})
+    h.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res["info"] = info.cpu().numpy()
+    return res
+
+
+def test_default_config_single_rod(h16, oracle16, torch_mod):
+    """BASELINE configs[0]: main.cpp default qe, N=16, plus stages 3-4 with F_tip=(0,0,-1), M_tip=0."""
+    K = oracle16.strain_from_modes(DEFAULT_QE)
+    F = np.array([[0.0, 0.0, -1.0]]); Mt = np.zeros((1, 3))
+    ref = oracle16.integrate_all(K, F, Mt)
+    got = _gpu_all(h16, torch_mod, K, F, Mt)
+    assert got["info"][0] == 0
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, s
+
+
+def test_modal_adapter_matches_oracle(h16, oracle16, torch_mod):
+    rng = np.random.default_rng(1)
+    for ne in (1, 2, 3, 5):
+        qe = rng.uniform(-2, 2, size=(64, 3 * ne))
+        Kref = oracle16.strain_from_modes(qe, ne)
+        Kgpu = h16.strain_from_modes(torch_mod.from_numpy(qe).cuda()).cpu().numpy()
+        assert rel_err(Kgpu, Kref) <= 1e-14
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 17, 1000, 10000])
+def test_random_batches_fused(h16, oracle16, torch_mod, batch):
+    """BASELINE configs[1]: random constant+linear strain fields, all four stages."""
+    K, F, Mt, fb = oracle16.generate_rods(0x5EED, 0, batch)
+    ref = oracle16.integrate_all(K, F, Mt, fbar=fb, explicit_inverse=True)
+    got = _gpu_all(h16, torch_mod, K, F, Mt, fbar=fb)
+    assert ref["bad"] == 0 and (got["info"] == 0).all()
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, s
+
+
+def test_generator_bit_exact(h16, oracle16, torch_mod):
+    B = 4097
+    K = torch_mod.empty((B, 3, 16), dtype=torch_mod.float64, device="cuda")
+    F = torch_mod.empty((B, 3), dtype=torch_mod.float64, device="cuda")
+    Mt = torch_mod.empty_like(F)
+    fb = torch_mod.empty_like(K)
+    h16.generate_rods(0x5EED, 123456789012, B, K, F, Mt, fb)
+    h16.synchronize()
+    Kr, Fr, Mr, fr = oracle16.generate_rods(0x5EED, 123456789012, B)
+    assert np.array_equal(K.cpu().numpy(), Kr)
+    assert np.array_equal(F.cpu().numpy(), Fr)
+    assert np.array_equal(Mt.cpu().numpy(), Mr)
+    assert np.array_equal(fb.cpu().numpy(), fr)
+
+
+def test_all_optional_inputs(h16, oracle16, torch_mod):
+    rng = np.random.default_rng(7)
+    B = 513
+    K, F, Mt, fb = oracle16.generate_rods(11, 0, B)
+    q0 = rng.normal(size=(B, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    r0 = rng.normal(size=(B, 3))
+    Gamma = np.concatenate([1 + 0.1 * rng.normal(size=(B, 1, 16)), 0.1 * rng.normal(size=(B, 2, 16))], axis=1)
+    fbar = rng.normal(size=(B, 3, 16)); lbar = rng.normal(size=(B, 3, 16))
+    ref = oracle16.integrate_all(K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fbar, lbar=lbar)
+    got = _gpu_all(h16, torch_mod, K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fbar, lbar=lbar)
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, s
+
+
+def test_separate_stage_calls_match_fused(h16, oracle16, torch_mod):
+    B = 777
+    K, F, Mt, fb = oracle16.generate_rods(3, 1000, B)
+    ref = oracle16.integrate_all(K, F, Mt, fbar=fb)
+    t = lambda a: torch_mod.from_numpy(a).cuda()
+    Q = h16.integrate_quaternions(t(K))
+    r = h16.integrate_position(Q)
+    n = h16.integrate_stress(t(F), fbar=t(fb))
+    m = h16.integrate_couple(Q, n, t(Mt))
+    h16.synchronize()
+    for name, val in (("Q", Q), ("r", r), ("n", n), ("m", m)):
+        assert rel_err(val.cpu().numpy(), ref[name]) <= TOL, name
+
+
+def test_host_buffers_through_c_abi(h16, oracle16):
+    """Plain host (numpy) buffers: the library stages them itself."""
+    B = 300
+    K, F, Mt, fb = oracle16.generate_rods(5, 0, B)
+    ref = oracle16.integrate_all(K, F, Mt, fbar=fb)
+    info = np.full(B, -1, dtype=np.int32)
+    got = h16.integrate_all(K, F, Mt, fbar=fb, info=info)
+    assert (info == 0).all()
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, s
+
+
+def test_empty_batch(h16):
+    K = np.empty((0, 3, 16)); F = np.empty((0, 3)); Mt = np.empty((0, 3))
+    out = h16.integrate_all(K, F, Mt)
+    assert out["Q"].shape == (0, 4, 15)
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 8, 12, 15])
+def test_small_node_counts(sri_lib, make_oracle, torch_mod, N):
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    o = make_oracle(N)
+    K, F, Mt, fb = o.generate_rods(9, 0, 257)
+    ref = o.integrate_all(K, F, Mt, fbar=fb)
+    with SpectralRodIntegrator(N, 0) as h:
+        got = _gpu_all(h, torch_mod, K, F, Mt, fbar=fb)
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, (N, s)
+
+
+def test_large_curvature_needs_pivoting(h16, oracle16, torch_mod):
+    """|K| up to ~70: the preconditioned operator is no longer diagonally dominant and row pivoting is exercised.
+    cond(A_NN) grows, so the CPU LU itself is only good to ~cond*eps; compare at 1e-10."""
+    rng = np.random.default_rng(5)
+    B = 2000
+    K = rng.uniform(-40, 40, size=(B, 3, 1)) + rng.uniform(-40, 40, size=(B, 3, 1)) * np.linspace(1, -1, 16)[None, None, :]
+    F = rng.uniform(-1, 1, size=(B, 3)); Mt = rng.uniform(-1, 1, size=(B, 3))
+    ref = oracle16.integrate_all(K, F, Mt, explicit_inverse=False)
+    got = _gpu_all(h16, torch_mod, K, F, Mt)
+    assert (got["info"] == 0).all()
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= 1e-10, s
+
+
+def test_shape_residual(h16, oracle16, torch_mod):
+    B = 400
+    K, F, Mt, fb = oracle16.generate_rods(21, 0, B)
+    ref = oracle16.integrate_all(K, F, Mt)
+    H = np.array([1.0, 1.0, 0.77])
+    rho_ref = oracle16.shape_residual(K, H, ref["Q"], ref["m"], Mt)
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    red = torch_mod.zeros(2, dtype=torch_mod.float64, device="cuda")
+    rho = h16.shape_residual(t(K), H, t(ref["Q"]), t(ref["m"]), t(Mt), reduce=red)
+    h16.synchronize()
+    assert rel_err(rho.cpu().numpy(), rho_ref) <= TOL
+    red = red.cpu().numpy()
+    assert abs(red[0] - (rho_ref ** 2).sum()) <= 1e-11 * (rho_ref ** 2).sum()
+    assert red[1] == np.abs(rho_ref).max() or abs(red[1] - np.abs(rho_ref).max()) <= 1e-12 * red[1]
