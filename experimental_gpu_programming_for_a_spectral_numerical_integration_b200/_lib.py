@@ -5,7 +5,10 @@ import ctypes
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libsri_cuda.so"
+import os
+
+# SRI_LIB_PATH lets kernel experiments (tools/) load an alternative build of the same C ABI
+LIB_PATH = Path(os.environ.get("SRI_LIB_PATH", Path(__file__).resolve().parent / "libsri_cuda.so"))
 
 SRI_OK = 0
 STATUS_NAMES = {
@@ -45,6 +48,7 @@ SYMBOLS = {
     "sri_create": (c_int, [c_int, c_int, POINTER(c_void_p)]),
     "sri_destroy": (c_int, [c_void_p]),
     "sri_set_stream": (c_int, [c_void_p, c_void_p]),
+    "sri_reset_stream": (c_int, [c_void_p]),
     "sri_synchronize": (c_int, [c_void_p]),
     "sri_get_N": (c_int, [c_void_p, POINTER(c_int)]),
     "sri_get_operator": (c_int, [c_void_p, c_int, c_void_p]),

@@ -121,8 +121,11 @@ class SpectralRodIntegrator:
     # -- plumbing
     def set_stream(self, stream) -> None:
         """Enqueue on a torch.cuda.Stream / raw cudaStream_t (None restores the handle's own stream)."""
-        raw = None if stream is None else int(getattr(stream, "cuda_stream", stream))
-        _lib.check(self._lib.sri_set_stream(self._h, raw), "sri_set_stream")
+        if stream is None:
+            _lib.check(self._lib.sri_reset_stream(self._h), "sri_reset_stream")
+            return
+        raw = int(getattr(stream, "cuda_stream", stream))
+        _lib.check(self._lib.sri_set_stream(self._h, raw if raw else None), "sri_set_stream")
 
     def use_current_torch_stream(self) -> None:
         self.set_stream(torch.cuda.current_stream(self.device))

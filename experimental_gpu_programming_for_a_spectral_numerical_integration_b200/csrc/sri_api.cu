@@ -341,7 +341,8 @@ int sri_create(int N, int device, sri_handle* out) {
         std::vector<double> t(L::total, 0.0);
         for (int j = 0; j < M; ++j)
             for (int i = 0; i < M; ++i) {
-                t[L::St + j * sri::MP16 + i] = h->ops.S[j * M + i];
+                t[L::St + j * sri::MP16 + i] = -0.5 * h->ops.S[j * M + i];
+                t[L::Sp + j * sri::MP16 + i] = h->ops.S[j * M + i];
                 t[L::STt + j * sri::MP16 + i] = h->ops.ST[j * M + i];
             }
         for (int i = 0; i < M; ++i) {
@@ -385,7 +386,13 @@ int sri_destroy(sri_handle h) {
 
 int sri_set_stream(sri_handle h, void* cuda_stream) {
     SRI_TRY(check_handle(h));
-    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SRI_OK;
+}
+
+int sri_reset_stream(sri_handle h) {
+    SRI_TRY(check_handle(h));
+    h->stream = h->own_stream;
     return SRI_OK;
 }
 

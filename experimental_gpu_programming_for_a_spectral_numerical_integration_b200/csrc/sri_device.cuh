@@ -25,6 +25,16 @@ __device__ __forceinline__ void q_sub_mul(quat& c, const quat& u, const quat& m)
     c.w = fma(u.z, m.z, c.w);  c.x = fma(u.z, m.y, c.x);  c.y = fma(-u.z, m.x, c.y); c.z = fma(-u.z, m.w, c.z);
 }
 
+// One of the four FMA levels of c -= u (x) m (level l consumes component l of u); the levels of several
+// independent updates can be interleaved to cover the FP64 pipe's dependent-issue latency.
+template <int LEVEL>
+__device__ __forceinline__ void q_sub_mul_level(quat& c, const quat& u, const quat& m) {
+    if (LEVEL == 0) { c.w = fma(-u.w, m.w, c.w); c.x = fma(-u.w, m.x, c.x); c.y = fma(-u.w, m.y, c.y); c.z = fma(-u.w, m.z, c.z); }
+    if (LEVEL == 1) { c.w = fma(u.x, m.x, c.w);  c.x = fma(-u.x, m.w, c.x); c.y = fma(u.x, m.z, c.y);  c.z = fma(-u.x, m.y, c.z); }
+    if (LEVEL == 2) { c.w = fma(u.y, m.y, c.w);  c.x = fma(-u.y, m.z, c.x); c.y = fma(-u.y, m.w, c.y); c.z = fma(u.y, m.x, c.z); }
+    if (LEVEL == 3) { c.w = fma(u.z, m.z, c.w);  c.x = fma(u.z, m.y, c.x);  c.y = fma(-u.z, m.x, c.y); c.z = fma(-u.z, m.w, c.z); }
+}
+
 // p (x) c
 __device__ __forceinline__ quat q_mul(const quat& p, const quat& c) {
     quat r;

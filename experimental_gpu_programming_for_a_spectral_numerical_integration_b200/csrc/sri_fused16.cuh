@@ -6,6 +6,17 @@
 //
 // Replaces, per rod: updateA (main.cpp:55-88), A_NN.inverse()*(b-ivp) (main.cpp:113), updatePositionb
 // (main.cpp:121-140), Dn_NN_inv*(b_NN-ivp) (main.cpp:172) and the two spec'd stages (rod_modeling.pdf 1.17-1.18).
+//
+// What shapes the code (measured on B200, tools/*microbench*, profiles/):
+//   * the FP64 pipe issues one warp-DFMA per 2 cycles per SM sub-partition but a dependent DFMA waits ~36 cycles,
+//     so every serial FP64 chain on the elimination's critical path is kept as short as possible (tree-shaped
+//     products, branch-free Newton reciprocal) and the pivot search / reciprocal of step k+1 is issued before the
+//     bulk update of step k so that it hides behind this warp's own DFMA stream;
+//   * a row lives in ONE lane, and getting it out costs the same LSU time whichever way (8.4 cycles per quaternion
+//     for a 2-lane shared-memory store + 4.2 for the loads, 8.2 for eight SHFL.IDX); shuffles need no barrier and
+//     keep each elimination step a single basic block the scheduler can software-pipeline, so shuffles it is;
+//   * per-rod inputs that are only needed after the elimination are prefetched with cp.async at the top of the
+//     iteration, as are the next pair's strain samples.
 #pragma once
 #include "sri_device.cuh"
 
@@ -13,15 +24,20 @@ namespace sri {
 
 constexpr int MP16 = 16;  // padded rows per rod in this kernel
 
+#ifndef SRI_MINBLOCKS
+#define SRI_MINBLOCKS 3
+#endif
+
 // Packed operator tables (doubles), stride MP16, zero padded.  Built on the host by sri_api.cu.
 struct OpsLayout16 {
-    static constexpr int St = 0;                   // [15][16]  St[j*16+i]  = (Dn_NN^-1)(i,j)
-    static constexpr int STt = St + 15 * MP16;     // [15][16]  STt[j*16+i] = (D_TT^-1)(i,j)
+    static constexpr int St = 0;                   // [15][16]  St[j*16+i]  = -1/2 (Dn_NN^-1)(i,j)   (pre-scaled)
+    static constexpr int Sp = St + 15 * MP16;      // [15][16]  Sp[j*16+i]  = (Dn_NN^-1)(i,j)
+    static constexpr int STt = Sp + 15 * MP16;     // [15][16]  STt[j*16+i] = (D_TT^-1)(i,j)
     static constexpr int g = STt + 15 * MP16;      // [16]  g  = -(Dn_NN^-1 Dn_IN)
     static constexpr int gT = g + MP16;            // [16]  gT = -(D_TT^-1 D_TI)
     static constexpr int DTI = gT + MP16;          // [16]  D_TI
     static constexpr int DnIN = DTI + MP16;        // [16]  Dn_IN
-    static constexpr int total = DnIN + MP16;      // 544 doubles
+    static constexpr int total = DnIN + MP16;      // 784 doubles
 };
 
 struct FusedParams {
@@ -45,81 +61,240 @@ struct FusedParams {
     int* info;
 };
 
-constexpr int kWarpScratch16 = 512;  // doubles of shared scratch per warp (4 KB)
+// Per-rod shared scratch (doubles).
+struct RodScratch {
+    static constexpr int kbuf = 0;              // [2][4][16] strain samples (double buffered): K0,K1,K2 rows + q0 row
+    static constexpr int fbar = kbuf + 128;     // [3][16]
+    static constexpr int lbar = fbar + 48;      // [3][16]
+    static constexpr int gam = lbar + 48;       // [3][16]
+    static constexpr int misc = gam + 48;       // [16]: F_tip 0..2, M_tip 3..5, r0 6..8
+    static constexpr int qnode = misc + 16;     // [16][4] quaternions by node (slot M = base node)
+    static constexpr int vec = qnode + 64;      // [16][4] nodal 3-vectors (r')
+    static constexpr int vec2 = vec + 64;       // [16][4]
+    static constexpr int pbuf = vec2 + 64;      // [2][16][4] pivot-row publish buffers (double buffered)
+    static constexpr int total = pbuf + 128;    // 608 doubles
+};
+constexpr int kWarpScratch16 = 2 * RodScratch::total;  // doubles per warp
 
-// One Gauss-Jordan step over the quaternions with implicit row pivoting, one row per lane; K is a compile-time
-// constant so that every access to c[] is a register.  pbuf: this half-warp's publish area, 2 x 16 slots x 4.
-template <int K>
-__device__ __forceinline__ void gj_step16(quat (&c)[15], quat& b, int row, double* pbuf, bool& used, int& mycol,
-                                          int& sing) {
-    // --- pivot search over the 16-lane segment: top bits of |c_ik|^2, row index in the low 4 bits
-    const double nrm = q_norm2(c[K]);
-    unsigned key = used ? 0u : ((((unsigned)__double2hiint(nrm)) & 0xFFFFFFF0u) | (unsigned)(15 - row));
+// ---- small PTX helpers --------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// Branch-free reciprocal: MUFU.RCP64H seed (~20 bits) and one cubically convergent correction
+// r <- r (1 + e + e^2), e = 1 - x r: three dependent FP64 operations instead of the ~8 of the IEEE division.
+// Relative error ~1e-16 (not correctly rounded; the elimination does not need it to be).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+// Broadcast of one quaternion from lane `src` (per half-warp) to every lane of that half.
+__device__ __forceinline__ quat shfl_quat(const quat& q, int src) {
+    quat r;
+    r.w = __shfl_sync(0xffffffffu, q.w, src);
+    r.x = __shfl_sync(0xffffffffu, q.x, src);
+    r.y = __shfl_sync(0xffffffffu, q.y, src);
+    r.z = __shfl_sync(0xffffffffu, q.z, src);
+    return r;
+}
+
+// p (x) c with each component evaluated as (t1 + t2) + (t3 + t4): dependent depth 3 instead of 4.
+__device__ __forceinline__ quat q_mul_tree(const quat& p, const quat& c) {
+    quat r;
+    r.w = fma(-p.x, c.x, p.w * c.w) - fma(p.z, c.z, p.y * c.y);
+    r.x = fma(p.x, c.w, p.w * c.x) + fma(-p.z, c.y, p.y * c.z);
+    r.y = fma(-p.x, c.z, p.w * c.y) + fma(p.z, c.x, p.y * c.w);
+    r.z = fma(p.x, c.y, p.w * c.z) + fma(p.z, c.w, -p.y * c.x);
+    return r;
+}
+
+// Pivot candidate of a row for column value c: key = top 28 bits of |c|^2 (monotone for non-negative doubles) with
+// the row index in the low 4 bits, so that the segment-wide maximum also names the winning lane; rows already
+// used as pivots get key 0.  cand = c^-1 = conj(c)/|c|^2, computed by EVERY lane for its own row while the
+// butterfly runs, so that the winner only has to broadcast it.
+__device__ __forceinline__ void pivot_candidate(const quat& c, bool used, int row, unsigned& key, quat& cand) {
+    const double nrm = fma(c.w, c.w, c.x * c.x) + fma(c.y, c.y, c.z * c.z);
+    key = used ? 0u : ((((unsigned)__double2hiint(nrm)) & 0xFFFFFFF0u) | (unsigned)(15 - row));
+    const double inv = fast_rcp(nrm);
+    cand.w = c.w * inv; cand.x = -c.x * inv; cand.y = -c.y * inv; cand.z = -c.z * inv;
+}
+
+// max over the 16-lane segment (xor offsets 8,4,2,1 never leave the half-warp)
+__device__ __forceinline__ unsigned segment_max16(unsigned key) {
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) {
         const unsigned other = __shfl_xor_sync(0xffffffffu, key, off);
         key = key > other ? key : other;
     }
+    return key;
+}
+
+#ifndef SRI_BCAST_SHFL
+#define SRI_BCAST_SHFL 0  // 0: pivot row through shared memory; 1: SHFL.IDX
+#endif
+#ifndef SRI_GROUP
+#define SRI_GROUP 3  // quaternion updates interleaved level by level
+#endif
+
+// One Gauss-Jordan step over the quaternions with implicit row pivoting, ROLLED form.
+//
+// B200's instruction supply sustains full FP64 rate only for loops of <= 32 KB of code (tools/icache_microbench:
+// 36 TF at 32 KB, 7-20 TF at 64 KB with de-synchronised warps), and a fully unrolled 15-step elimination is ~86 KB.
+// So the row is kept in a sliding window instead: slot 0 always holds the pivot column of the current step, every
+// update writes its result one slot down (c[j-1] = c[j] - u_j (x) m; the shift costs no instruction), and the same
+// body serves several steps.  L = number of window slots the body touches; a body may run while the live width
+// 15-k is <= L (the slots beyond it hold zeros and stay zero).  Four bodies (L = 15, 11, 7, 3) cost 17 % more
+// quaternion updates than the exact triangle and fit the whole kernel in the instruction cache.
+//
+//   equations:  sum_j Q_j (x) c_ij = b_i.   Row i takes  c_ij -= u_j (x) m_i  with u = pivot row and
+//   m_i = c_pk^-1 (x) c_ik; the pivot row takes m_p = 1 - c_pk^-1, which normalises it with the same update.
+// On entry key/cand describe slot 0 (key already segment-reduced); on exit they describe the new slot 0.
+template <int L>
+__device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, int row, double* pbuf, bool& used,
+                                               int& mycol, int& sing, unsigned& key, quat& cand) {
     const int prow = 15 - (int)(key & 15u);
     const bool is_pivot = (row == prow) && !used;
-    if ((key >> 4) == 0u && sing == 0) sing = K + 1;
-    // --- the pivot lane publishes its row (columns K.. and the rhs)
-    double* buf = pbuf + (K & 1) * (MP16 * 4);
+    if ((key >> 4) == 0u && sing == 0) sing = k + 1;
+#if SRI_BCAST_SHFL
+    const int src = ((threadIdx.x & 16) | prow);
+#define SRI_PIVOT_ROW(j) shfl_quat(c[j], src)
+#define SRI_PIVOT_RHS() shfl_quat(b, src)
+    const quat pinv = shfl_quat(cand, src);
+#else
+    // the pivot lane publishes c_pk^-1 (slot 0), its window (slots 1..L-1) and its rhs (slot 15)
+    double* buf = pbuf + (k & 1) * (16 * 4);
     if (is_pivot) {
+        st_quat(buf, cand);
 #pragma unroll
-        for (int j = K; j < 15; ++j) st_quat(buf + 4 * j, c[j]);
+        for (int j = 1; j < L; ++j) st_quat(buf + 4 * j, c[j]);
         st_quat(buf + 4 * 15, b);
     }
     __syncwarp();
-    // --- multiplier: m = c_pk^-1 (x) c_ik; the pivot lane takes 1 - c_pk^-1 so that the same update
-    //     normalises its own row
-    const quat piv = ld_quat(buf + 4 * K);
-    const double inv = 1.0 / q_norm2(piv);
-    quat pinv;
-    pinv.w = piv.w * inv; pinv.x = -piv.x * inv; pinv.y = -piv.y * inv; pinv.z = -piv.z * inv;
-    quat mlt = q_mul(pinv, c[K]);
-    if (is_pivot) { mlt.w = 1.0 - pinv.w; mlt.x = -pinv.x; mlt.y = -pinv.y; mlt.z = -pinv.z; mycol = K; used = true; }
-    // --- rank-1 update of the trailing columns and of the rhs
+#define SRI_PIVOT_ROW(j) ld_quat(buf + 4 * (j))
+#define SRI_PIVOT_RHS() ld_quat(buf + 4 * 15)
+    const quat pinv = ld_quat(buf);
+#endif
+    quat mlt = q_mul_tree(pinv, c[0]);
+    if (is_pivot) { mlt.w = 1.0 - pinv.w; mlt.x = -pinv.x; mlt.y = -pinv.y; mlt.z = -pinv.z; mycol = k; used = true; }
+    // Items 0..L-1 of this step: item t < L-1 is window slot t+1 (result goes to slot t), item L-1 is the rhs.
+    // A dependent DFMA waits ~36 cycles while the pipe takes a new one every 2, so items are processed in groups of
+    // SRI_GROUP with their four FMA levels interleaved (SRI_GROUP x 4 independent chains in flight per warp).
+    // The first group contains slot 1, the next pivot column: its candidate and the butterfly follow immediately
+    // and hide behind the remaining groups.
+    unsigned other = 0u;
+    int stage_done = 0;
 #pragma unroll
-    for (int j = K + 1; j < 15; ++j) {
-        const quat u = ld_quat(buf + 4 * j);
-        q_sub_mul(c[j], u, mlt);
+    for (int t0 = 0; t0 < L; t0 += SRI_GROUP) {
+        quat u[SRI_GROUP], acc[SRI_GROUP];
+#pragma unroll
+        for (int g = 0; g < SRI_GROUP; ++g) {
+            const int t = t0 + g;
+            if (t < L - 1) { u[g] = SRI_PIVOT_ROW(t + 1 < 15 ? t + 1 : 14); acc[g] = c[t + 1 < 15 ? t + 1 : 14]; }
+            else if (t == L - 1) { u[g] = SRI_PIVOT_RHS(); acc[g] = b; }
+        }
+#pragma unroll
+        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<0>(acc[g], u[g], mlt);
+#pragma unroll
+        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<1>(acc[g], u[g], mlt);
+#pragma unroll
+        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<2>(acc[g], u[g], mlt);
+#pragma unroll
+        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<3>(acc[g], u[g], mlt);
+#pragma unroll
+        for (int g = 0; g < SRI_GROUP; ++g) {
+            const int t = t0 + g;
+            if (t < L - 1) c[t < 15 ? t : 14] = acc[g];
+            else if (t == L - 1) b = acc[g];
+        }
+        if (t0 == 0) {
+            if (L == 1) { c[0].w = 0.0; c[0].x = 0.0; c[0].y = 0.0; c[0].z = 0.0; }
+            pivot_candidate(c[0], used, row, key, cand);
+        } else if (stage_done < 4) {
+            // two butterfly stages per later group
+            other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage_done); key = key > other ? key : other; ++stage_done;
+            if (stage_done < 4) { other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage_done); key = key > other ? key : other; ++stage_done; }
+        }
     }
-    {
-        const quat u = ld_quat(buf + 4 * 15);
-        q_sub_mul(b, u, mlt);
+#pragma unroll
+    for (int stage = 0; stage < 4; ++stage) {
+        if (stage >= stage_done) {
+            other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage);
+            key = key > other ? key : other;
+        }
     }
+    if (L > 1) { c[L - 1].w = 0.0; c[L - 1].x = 0.0; c[L - 1].y = 0.0; c[L - 1].z = 0.0; }
+#undef SRI_PIVOT_ROW
+#undef SRI_PIVOT_RHS
 }
 
-// Full elimination.  MS = 15: static size; MS = 0: runtime M <= 15 (steps K >= M are skipped; the padded rows and
-// columns are zero).  On return b holds Q_{mycol}.
-template <int MS>
+// Full elimination of an M x M system, M <= 15 at run time (rows and columns >= M are zero padding and never
+// pivot).  On return b holds Q_{mycol}.
 __device__ __forceinline__ void gauss_jordan16(quat (&c)[15], quat& b, int M, int row, double* pbuf, int& mycol,
                                                int& sing) {
     bool used = (row >= M);
     mycol = row;
     sing = 0;
-#define SRI_GJ_STEP(K) if (MS != 0 || K < M) gj_step16<K>(c, b, row, pbuf, used, mycol, sing);
-    SRI_GJ_STEP(0) SRI_GJ_STEP(1) SRI_GJ_STEP(2) SRI_GJ_STEP(3) SRI_GJ_STEP(4)
-    SRI_GJ_STEP(5) SRI_GJ_STEP(6) SRI_GJ_STEP(7) SRI_GJ_STEP(8) SRI_GJ_STEP(9)
-    SRI_GJ_STEP(10) SRI_GJ_STEP(11) SRI_GJ_STEP(12) SRI_GJ_STEP(13) SRI_GJ_STEP(14)
-#undef SRI_GJ_STEP
+    unsigned key;
+    quat cand;
+    pivot_candidate(c[0], used, row, key, cand);
+    key = segment_max16(key);
+    int k = 0;
+    const int e0 = M < 4 ? M : 4, e1 = M < 8 ? M : 8, e2 = M < 12 ? M : 12;
+#pragma unroll 1
+    for (; k < e0; ++k) gj_step_rolled<15>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+#pragma unroll 1
+    for (; k < e1; ++k) gj_step_rolled<11>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+#pragma unroll 1
+    for (; k < e2; ++k) gj_step_rolled<7>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+#pragma unroll 1
+    for (; k < M; ++k) gj_step_rolled<3>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+}
+
+// out_c = sum_j T[j*16+row] * v[j][c], c = 0..2, with three interleaved partial sums per component so that the
+// dependent DFMA chains are 5 long instead of 15.
+template <int MS>
+__device__ __forceinline__ void contract16(const double* T, const double* v, int M, int row, double& o0, double& o1,
+                                           double& o2) {
+    double a[3][3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { a[s][0] = 0.0; a[s][1] = 0.0; a[s][2] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 15; ++j) {
+        if (MS == 0 && j >= M) break;
+        const double t = T[j * MP16 + row];
+        const double2 v01 = *reinterpret_cast<const double2*>(v + 4 * j);
+        const double v2 = v[4 * j + 2];
+        a[j % 3][0] = fma(t, v01.x, a[j % 3][0]);
+        a[j % 3][1] = fma(t, v01.y, a[j % 3][1]);
+        a[j % 3][2] = fma(t, v2, a[j % 3][2]);
+    }
+    o0 = (a[0][0] + a[1][0]) + a[2][0];
+    o1 = (a[0][1] + a[1][1]) + a[2][1];
+    o2 = (a[0][2] + a[1][2]) + a[2][2];
 }
 
 // SOLVE = true: all stages starting from the strain samples K.  SOLVE = false: the cached-operator stages only
 // (position / stress / couple), reading Q (and optionally n) produced by an earlier call.
 template <int MS, bool SOLVE>
-__global__ void __launch_bounds__(128) fused16_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(128, SOLVE ? SRI_MINBLOCKS : 4) fused16_kernel(const FusedParams p) {
     extern __shared__ __align__(16) double smem[];
-    double* tab = smem;                                        // OpsLayout16::total doubles
+    double* tab = smem;  // OpsLayout16::total doubles
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane >> 4, row = lane & 15;
-    double* wscr = smem + OpsLayout16::total + warp * kWarpScratch16;
-    double* pbuf = wscr + sub * 128;        // [2][16][4]   publish buffers of this half-warp
-    double* qnode = wscr + 256 + sub * 64;  // [16][4]      quaternions by node (slot M = base node)
-    double* vec = wscr + 384 + sub * 64;    // [16][4]      nodal 3-vectors
-    double* vec2 = pbuf;                    // reused after the elimination
-    double* vec3 = pbuf + 64;
+    double* scr = smem + OpsLayout16::total + warp * kWarpScratch16 + sub * RodScratch::total;
+    double* qnode = scr + RodScratch::qnode;
+    double* vec = scr + RodScratch::vec;
+    double* vec2 = scr + RodScratch::vec2;
+    double* misc = scr + RodScratch::misc;
 
     for (int i = threadIdx.x; i < OpsLayout16::total; i += blockDim.x) tab[i] = p.ops[i];
     __syncthreads();
@@ -128,47 +303,83 @@ __global__ void __launch_bounds__(128) fused16_kernel(const FusedParams p) {
     const int N = M + 1;
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
     const long long pairs = (p.batch + 1) >> 1;
+    const long long pair0 = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
 
-    for (long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + warp; pair < pairs; pair += warps_total) {
+    // strain samples (and q0) of rod `rod_` -> kbuf[slot]; lanes outside the rod / batch write zeros (q0: identity)
+    auto prefetch_K = [&](long long rod_, int slot) {
+        double* kb = scr + RodScratch::kbuf + slot * 64;
+        const bool ok = rod_ < p.batch;
+        if (SOLVE) {
+            if (ok && row < N) {
+                const double* s = p.K + rod_ * 3 * N + row;
+                cp_async8(kb + row, s); cp_async8(kb + 16 + row, s + N); cp_async8(kb + 32 + row, s + 2 * N);
+            } else {
+                kb[row] = 0.0; kb[16 + row] = 0.0; kb[32 + row] = 0.0;
+            }
+        }
+        if (row < 4) {
+            if (ok && p.q0) cp_async8(kb + 48 + row, p.q0 + rod_ * 4 + row);
+            else kb[48 + row] = (row == 0) ? 1.0 : 0.0;
+        }
+    };
+
+    if (pair0 < pairs) prefetch_K(2 * pair0 + sub, 0);
+    cp_async_commit();
+
+    int it = 0;
+    for (long long pair = pair0; pair < pairs; pair += warps_total, ++it) {
         const long long rod = 2 * pair + sub;
         const bool live = rod < p.batch;
+        const int cur = it & 1;
 
-        // ---- inputs -----------------------------------------------------------------------------------
-        quat q0; q0.w = 1.0; q0.x = 0.0; q0.y = 0.0; q0.z = 0.0;
-        if (p.q0 && live) { const double* s = p.q0 + rod * 4; q0.w = s[0]; q0.x = s[1]; q0.y = s[2]; q0.z = s[3]; }
+        // ---- prefetch: this pair's late inputs and the next pair's strain samples -----------------------
+        if (live && row < N) {
+            if (p.fbar) { const double* s = p.fbar + rod * 3 * N + row; double* d = scr + RodScratch::fbar + row;
+                          cp_async8(d, s); cp_async8(d + 16, s + N); cp_async8(d + 32, s + 2 * N); }
+            if (p.lbar) { const double* s = p.lbar + rod * 3 * N + row; double* d = scr + RodScratch::lbar + row;
+                          cp_async8(d, s); cp_async8(d + 16, s + N); cp_async8(d + 32, s + 2 * N); }
+            if (p.Gamma) { const double* s = p.Gamma + rod * 3 * N + row; double* d = scr + RodScratch::gam + row;
+                           cp_async8(d, s); cp_async8(d + 16, s + N); cp_async8(d + 32, s + 2 * N); }
+        }
+        if (live && row < 3) {
+            if (p.F_tip) cp_async8(misc + row, p.F_tip + rod * 3 + row);
+            if (p.M_tip) cp_async8(misc + 3 + row, p.M_tip + rod * 3 + row);
+            if (p.r0) cp_async8(misc + 6 + row, p.r0 + rod * 3 + row);
+        }
+        if (pair + warps_total < pairs) prefetch_K(2 * (pair + warps_total) + sub, cur ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed: this pair's K and q0 have landed
+        __syncwarp();
+
+        const double* kb = scr + RodScratch::kbuf + cur * 64;
+        quat q0;
+        {
+            const double2 a = *reinterpret_cast<const double2*>(kb + 48);
+            const double2 c2 = *reinterpret_cast<const double2*>(kb + 50);
+            q0.w = a.x; q0.x = a.y; q0.y = c2.x; q0.z = c2.y;
+        }
         quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
         if (SOLVE) {
-            {
-                quat ks; ks.w = 0.0; ks.x = 0.0; ks.y = 0.0; ks.z = 0.0;
-                if (live && row < M) {
-                    const double* s = p.K + rod * 3 * N + row;
-                    ks.x = -0.5 * s[0]; ks.y = -0.5 * s[N]; ks.z = -0.5 * s[2 * N];
-                }
-                st_quat(vec + 4 * row, ks);
-            }
-            __syncwarp();
-
             // ---- stage 1: assemble c_ij = delta_ij - 1/2 S_ij (0,K_j) and eliminate ---------------------
             quat c[15], b;
 #pragma unroll
             for (int j = 0; j < 15; ++j) {
-                const double s = tab[OpsLayout16::St + j * MP16 + row];
-                const quat kq = ld_quat(vec + 4 * j);
+                const double s = tab[OpsLayout16::St + j * MP16 + row];  // -1/2 S_ij
                 c[j].w = (j == row) ? 1.0 : 0.0;
-                c[j].x = s * kq.x; c[j].y = s * kq.y; c[j].z = s * kq.z;
+                c[j].x = s * kb[j]; c[j].y = s * kb[16 + j]; c[j].z = s * kb[32 + j];
             }
             {
                 const double gi = tab[OpsLayout16::g + row];
                 b.w = gi * q0.w; b.x = gi * q0.x; b.y = gi * q0.y; b.z = gi * q0.z;
             }
             int mycol, sing;
-            gauss_jordan16<MS>(c, b, M, row, pbuf, mycol, sing);
+            gauss_jordan16(c, b, M, row, scr + RodScratch::pbuf, mycol, sing);
             __syncwarp();
             if (row < M) st_quat(qnode + 4 * mycol, b);
             if (row == M) st_quat(qnode + 4 * M, q0);
-            __syncwarp();
             if (p.info && live && row == 0) p.info[rod] = sing;
-
+            cp_async_wait<0>();
+            __syncwarp();
             if (row <= M) q = ld_quat(qnode + 4 * row);
             if (p.Q && live && row < M) {
                 double* d = p.Q + rod * 4 * M + row;
@@ -180,106 +391,93 @@ __global__ void __launch_bounds__(128) fused16_kernel(const FusedParams p) {
                 const double* s = p.Qin + rod * 4 * M + row;
                 q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M];
             }
-        }
-        if (!(p.r || p.n || p.m)) { __syncwarp(); continue; }
-
-        // ---- stage 2: r = S (R(q) Gamma) + g r0 ---------------------------------------------------------
-        double bv0 = 0.0, bv1 = 0.0, bv2 = 0.0;
-        if (row <= M) {
-            if (p.Gamma && live) {
-                const double* s = p.Gamma + rod * 3 * N + row;
-                q_rotate(q, s[0], s[N], s[2 * N], bv0, bv1, bv2);
-            } else {
-                q_rotate_e1(q, bv0, bv1, bv2);
-            }
-        }
-        {
-            quat t; t.w = bv0; t.x = bv1; t.y = bv2; t.z = 0.0;
-            st_quat(vec + 4 * row, t);
-        }
-        __syncwarp();
-        if (p.r) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-            for (int j = 0; j < 15; ++j) {
-                if (MS == 0 && j >= M) break;
-                const double s = tab[OpsLayout16::St + j * MP16 + row];
-                const quat t = ld_quat(vec + 4 * j);
-                a0 = fma(s, t.w, a0); a1 = fma(s, t.x, a1); a2 = fma(s, t.y, a2);
-            }
-            if (p.r0 && live) {
-                const double gi = tab[OpsLayout16::g + row];
-                const double* s = p.r0 + rod * 3;
-                a0 = fma(gi, s[0], a0); a1 = fma(gi, s[1], a1); a2 = fma(gi, s[2], a2);
-            }
-            if (live && row < M) {
-                double* d = p.r + rod * 3 * M + row;
-                d[0] = a0; d[M] = a1; d[2 * M] = a2;
-            }
-        }
-        if (!(p.n || p.m)) { __syncwarp(); continue; }
-
-        // ---- stage 3: n = D_TT^-1 (-fbar - D_TI F_tip^T); lane `row` = reduced index (node row+1) -------
-        double F0 = 0.0, F1 = 0.0, F2 = 0.0;
-        if (live) { const double* s = p.F_tip + rod * 3; F0 = s[0]; F1 = s[1]; F2 = s[2]; }
-        double n0, n1, n2;
-        if (!SOLVE && p.nin) {
-            n0 = 0.0; n1 = 0.0; n2 = 0.0;
-            if (live && row < M) { const double* s = p.nin + rod * 3 * M + row; n0 = s[0]; n1 = s[M]; n2 = s[2 * M]; }
-        } else if (p.fbar) {
-            const double dti = tab[OpsLayout16::DTI + row];
-            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-            if (live && row < M) { const double* s = p.fbar + rod * 3 * N + row + 1; f0 = s[0]; f1 = s[N]; f2 = s[2 * N]; }
-            quat t; t.w = -f0 - dti * F0; t.x = -f1 - dti * F1; t.y = -f2 - dti * F2; t.z = 0.0;
-            st_quat(vec2 + 4 * row, t);
+            cp_async_wait<0>();
             __syncwarp();
-            n0 = 0.0; n1 = 0.0; n2 = 0.0;
-#pragma unroll
-            for (int j = 0; j < 15; ++j) {
-                if (MS == 0 && j >= M) break;
-                const double s = tab[OpsLayout16::STt + j * MP16 + row];
-                const quat u = ld_quat(vec2 + 4 * j);
-                n0 = fma(s, u.w, n0); n1 = fma(s, u.x, n1); n2 = fma(s, u.y, n2);
-            }
-        } else {
-            const double gi = tab[OpsLayout16::gT + row];
-            n0 = gi * F0; n1 = gi * F1; n2 = gi * F2;
         }
-        if (p.n && live && row < M) {
-            double* d = p.n + rod * 3 * M + row;
-            d[0] = n0; d[M] = n1; d[2 * M] = n2;
-        }
-        if (!p.m) { __syncwarp(); continue; }
 
-        // ---- stage 4: m = D_TT^-1 (-(r' x n + lbar) - D_TI M_tip^T) ------------------------------------
-        {
-            double T0 = 0.0, T1 = 0.0, T2 = 0.0;
-            if (live) { const double* s = p.M_tip + rod * 3; T0 = s[0]; T1 = s[1]; T2 = s[2]; }
-            const int nb = (row < M) ? row + 1 : row;  // node of this reduced row
-            const quat rp = ld_quat(vec + 4 * nb);     // r' at that node (w,x,y = components)
-            double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-            if (p.lbar && live && row < M) { const double* s = p.lbar + rod * 3 * N + row + 1; l0 = s[0]; l1 = s[N]; l2 = s[2 * N]; }
-            const double dti = tab[OpsLayout16::DTI + row];
-            const double c0 = rp.x * n2 - rp.y * n1, c1 = rp.y * n0 - rp.w * n2, c2 = rp.w * n1 - rp.x * n0;
-            quat t; t.w = -(c0 + l0) - dti * T0; t.x = -(c1 + l1) - dti * T1; t.y = -(c2 + l2) - dti * T2; t.z = 0.0;
-            if (row >= M) { t.w = 0.0; t.x = 0.0; t.y = 0.0; }
-            st_quat(vec3 + 4 * row, t);
-            __syncwarp();
-            double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-#pragma unroll
-            for (int j = 0; j < 15; ++j) {
-                if (MS == 0 && j >= M) break;
-                const double s = tab[OpsLayout16::STt + j * MP16 + row];
-                const quat u = ld_quat(vec3 + 4 * j);
-                m0 = fma(s, u.w, m0); m1 = fma(s, u.x, m1); m2 = fma(s, u.y, m2);
+        if (p.r || p.n || p.m) {
+            // ---- stage 2: r = S (R(q) Gamma) + g r0 -----------------------------------------------------
+            double bv0 = 0.0, bv1 = 0.0, bv2 = 0.0;
+            if (row <= M) {
+                if (p.Gamma && live) {
+                    const double* gm = scr + RodScratch::gam + row;
+                    q_rotate(q, gm[0], gm[16], gm[32], bv0, bv1, bv2);
+                } else {
+                    q_rotate_e1(q, bv0, bv1, bv2);
+                }
             }
-            if (live && row < M) {
-                double* d = p.m + rod * 3 * M + row;
-                d[0] = m0; d[M] = m1; d[2 * M] = m2;
+            {
+                quat t; t.w = bv0; t.x = bv1; t.y = bv2; t.z = 0.0;
+                st_quat(vec + 4 * row, t);
+            }
+            // ---- stage 3 right-hand side (independent of stage 2; issued before the barrier) -----------
+            double F0 = 0.0, F1 = 0.0, F2 = 0.0;
+            if ((p.n || p.m) && live && p.F_tip) { F0 = misc[0]; F1 = misc[1]; F2 = misc[2]; }
+            const bool contract3 = (p.n || p.m) && p.fbar && !(!SOLVE && p.nin);
+            if (contract3) {
+                const double dti = tab[OpsLayout16::DTI + row];
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+                if (live && row < M) { const double* s = scr + RodScratch::fbar + row + 1; f0 = s[0]; f1 = s[16]; f2 = s[32]; }
+                quat t; t.w = -f0 - dti * F0; t.x = -f1 - dti * F1; t.y = -f2 - dti * F2; t.z = 0.0;
+                st_quat(vec2 + 4 * row, t);
+            }
+            __syncwarp();
+            if (p.r) {
+                double a0, a1, a2;
+                contract16<MS>(tab + OpsLayout16::Sp, vec, M, row, a0, a1, a2);
+                if (p.r0 && live) {
+                    const double gi = tab[OpsLayout16::g + row];
+                    a0 = fma(gi, misc[6], a0); a1 = fma(gi, misc[7], a1); a2 = fma(gi, misc[8], a2);
+                }
+                if (live && row < M) {
+                    double* d = p.r + rod * 3 * M + row;
+                    d[0] = a0; d[M] = a1; d[2 * M] = a2;
+                }
+            }
+            if (p.n || p.m) {
+                // ---- stage 3: n = D_TT^-1 (-fbar - D_TI F_tip^T); lane `row` = reduced index (node row+1)
+                double n0, n1, n2;
+                if (!SOLVE && p.nin) {
+                    n0 = 0.0; n1 = 0.0; n2 = 0.0;
+                    if (live && row < M) { const double* s = p.nin + rod * 3 * M + row; n0 = s[0]; n1 = s[M]; n2 = s[2 * M]; }
+                } else if (contract3) {
+                    contract16<MS>(tab + OpsLayout16::STt, vec2, M, row, n0, n1, n2);
+                } else {
+                    const double gi = tab[OpsLayout16::gT + row];
+                    n0 = gi * F0; n1 = gi * F1; n2 = gi * F2;
+                }
+                if (p.n && live && row < M) {
+                    double* d = p.n + rod * 3 * M + row;
+                    d[0] = n0; d[M] = n1; d[2 * M] = n2;
+                }
+                if (p.m) {
+                    // ---- stage 4: m = D_TT^-1 (-(r' x n + lbar) - D_TI M_tip^T) ------------------------
+                    double T0 = 0.0, T1 = 0.0, T2 = 0.0;
+                    if (live) { T0 = misc[3]; T1 = misc[4]; T2 = misc[5]; }
+                    const int nb = (row < M) ? row + 1 : row;  // node of this reduced row
+                    const double2 rp01 = *reinterpret_cast<const double2*>(vec + 4 * nb);
+                    const double rp2 = vec[4 * nb + 2];
+                    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+                    if (p.lbar && live && row < M) { const double* s = scr + RodScratch::lbar + row + 1; l0 = s[0]; l1 = s[16]; l2 = s[32]; }
+                    const double dti = tab[OpsLayout16::DTI + row];
+                    const double c0 = rp01.y * n2 - rp2 * n1, c1 = rp2 * n0 - rp01.x * n2, c2 = rp01.x * n1 - rp01.y * n0;
+                    quat t; t.w = -(c0 + l0) - dti * T0; t.x = -(c1 + l1) - dti * T1; t.y = -(c2 + l2) - dti * T2; t.z = 0.0;
+                    if (row >= M) { t.w = 0.0; t.x = 0.0; t.y = 0.0; }
+                    __syncwarp();  // every lane has read vec2 (stage 3) before it is overwritten
+                    st_quat(vec2 + 4 * row, t);
+                    __syncwarp();
+                    double m0, m1, m2;
+                    contract16<MS>(tab + OpsLayout16::STt, vec2, M, row, m0, m1, m2);
+                    if (live && row < M) {
+                        double* d = p.m + rod * 3 * M + row;
+                        d[0] = m0; d[M] = m1; d[2 * M] = m2;
+                    }
+                }
             }
         }
-        __syncwarp();
+        __syncwarp();  // scratch is reused by the next iteration
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace sri

@@ -62,9 +62,11 @@ int sri_phi(int na, int ne, double X, double begin, double end, double* out_colm
  * 157-160) and uploads it to `device`.  2 <= N <= 64. */
 int sri_create(int N, int device, sri_handle* out);
 int sri_destroy(sri_handle h);
-/* Work is enqueued on this CUDA stream (a cudaStream_t passed as void*); default: a stream owned by the handle.
+/* Work is enqueued on this CUDA stream (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * A new handle uses a non-blocking stream it owns; sri_reset_stream returns to it.
  * Calls with host buffers synchronise the stream before returning; calls with device buffers do not. */
 int sri_set_stream(sri_handle h, void* cuda_stream);
+int sri_reset_stream(sri_handle h);
 int sri_synchronize(sri_handle h);
 int sri_get_N(sri_handle h, int* N);
 /* Copies one cached operator to a host buffer.  which: 0 Dn (N*N), 1 Dn_NN (M*M), 2 Dn_IN (M),
