@@ -100,6 +100,8 @@ class SpectralRodIntegrator:
         self.N = int(N)
         self.M = self.N - 1
         self.device = int(device)
+        self._explicit_stream = False
+        self._torch_stream = None
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
@@ -123,9 +125,25 @@ class SpectralRodIntegrator:
         """Enqueue on a torch.cuda.Stream / raw cudaStream_t (None restores the handle's own stream)."""
         if stream is None:
             _lib.check(self._lib.sri_reset_stream(self._h), "sri_reset_stream")
+            self._explicit_stream = False
+            self._torch_stream = None
             return
         raw = int(getattr(stream, "cuda_stream", stream))
         _lib.check(self._lib.sri_set_stream(self._h, raw if raw else None), "sri_set_stream")
+        self._explicit_stream = True
+
+    def _follow_torch(self, *tensors) -> None:
+        """Unless a stream was set explicitly, enqueue on torch's current stream whenever a CUDA tensor is passed, so
+        that this library's kernels are ordered after the torch work that produced their inputs."""
+        if self._explicit_stream or torch is None:
+            return
+        for x in tensors:
+            if x is not None and _is_torch(x) and x.is_cuda:
+                cur = torch.cuda.current_stream(x.device).cuda_stream
+                if cur != self._torch_stream:
+                    _lib.check(self._lib.sri_set_stream(self._h, cur if cur else None), "sri_set_stream")
+                    self._torch_stream = cur
+                return
 
     def use_current_torch_stream(self) -> None:
         self.set_stream(torch.cuda.current_stream(self.device))
@@ -144,6 +162,7 @@ class SpectralRodIntegrator:
     # -- stages
     def strain_from_modes(self, qe, out=None):
         """qe [batch][3*ne] -> K [batch][3][N] (Phi<3,ne>(x_i)*qe, main.cpp:69)."""
+        self._follow_torch(qe)
         batch = qe.shape[0]
         ne = qe.shape[1] // 3
         K = out if out is not None else _empty_like_kind(qe, (batch, 3, self.N))
@@ -151,6 +170,7 @@ class SpectralRodIntegrator:
         return K
 
     def integrate_quaternions(self, K, q0=None, out=None, info=None):
+        self._follow_torch(K)
         batch = K.shape[0]
         Q = out if out is not None else _empty_like_kind(K, (batch, 4, self.M))
         _lib.check(
@@ -160,6 +180,7 @@ class SpectralRodIntegrator:
         return Q
 
     def integrate_position(self, Q, Gamma=None, r0=None, out=None):
+        self._follow_torch(Q)
         batch = Q.shape[0]
         r = out if out is not None else _empty_like_kind(Q, (batch, 3, self.M))
         _lib.check(
@@ -169,6 +190,7 @@ class SpectralRodIntegrator:
         return r
 
     def integrate_stress(self, F_tip, fbar=None, out=None):
+        self._follow_torch(F_tip)
         batch = F_tip.shape[0]
         n = out if out is not None else _empty_like_kind(F_tip, (batch, 3, self.M))
         _lib.check(
@@ -178,6 +200,7 @@ class SpectralRodIntegrator:
         return n
 
     def integrate_couple(self, Q, n, M_tip, q0=None, Gamma=None, lbar=None, out=None):
+        self._follow_torch(Q)
         batch = Q.shape[0]
         m = out if out is not None else _empty_like_kind(Q, (batch, 3, self.M))
         _lib.check(
@@ -191,6 +214,7 @@ class SpectralRodIntegrator:
     def integrate_all(self, K, F_tip=None, M_tip=None, q0=None, r0=None, Gamma=None, fbar=None, lbar=None,
                       Q=None, r=None, n=None, m=None, info=None, want=("Q", "r", "n", "m")):
         """Fused four-stage integration.  Returns a dict with the requested outputs (allocated if not given)."""
+        self._follow_torch(K)
         batch = K.shape[0]
         outs = {"Q": Q, "r": r, "n": n, "m": m}
         shapes = {"Q": (batch, 4, self.M), "r": (batch, 3, self.M), "n": (batch, 3, self.M), "m": (batch, 3, self.M)}
@@ -207,6 +231,7 @@ class SpectralRodIntegrator:
         return {k: v for k, v in outs.items() if v is not None}
 
     def shape_residual(self, K, H_diag, Q, m, M_tip, K0=None, q0=None, rho=None, reduce=None):
+        self._follow_torch(K)
         batch = K.shape[0]
         H = np.ascontiguousarray(np.asarray(H_diag, dtype=np.float64))
         if rho is None:
@@ -220,6 +245,7 @@ class SpectralRodIntegrator:
         return rho
 
     def generate_rods(self, seed: int, first_rod: int, batch: int, K=None, F_tip=None, M_tip=None, fbar=None):
+        self._follow_torch(K, F_tip, M_tip, fbar)
         _lib.check(
             self._lib.sri_generate_rods(self._h, seed, first_rod, batch, _ptr(K, "K"), _ptr(F_tip, "F_tip"),
                                         _ptr(M_tip, "M_tip"), _ptr(fbar, "fbar")),

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "sri_fused16.cuh"
+#include "sri_generic.cuh"
 #include "sri_host_math.hpp"
 
 namespace {
@@ -37,7 +38,10 @@ struct sri_context {
     cudaStream_t own_stream = nullptr;
     int sm_count = 0;
     sri_host::OperatorSet ops;
-    double* d_ops16 = nullptr;   // OpsLayout16 tables (N <= 16)
+    double* d_ops16 = nullptr;   // OpsLayout16 tables (N <= 16) or OpsLayoutGeneric tables (N > 16)
+    int R = 0;                   // generic kernel: row lanes (32 or 64); 0 for the N <= 16 kernel
+    size_t generic_smem = 0;
+    int generic_blocks_per_sm = 0;
     double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     int fused_blocks_per_sm = 0;
@@ -252,8 +256,22 @@ constexpr int kFusedThreads = 128;
 constexpr size_t kFusedSmem = (sri::OpsLayout16::total + (kFusedThreads / 32) * sri::kWarpScratch16) * sizeof(double);
 
 template <bool SOLVE>
+int launch_generic(sri_context* h, const sri::FusedParams& p) {
+    const long long cap = (long long)h->sm_count * h->generic_blocks_per_sm;
+    const int grid = (int)(p.batch < cap ? p.batch : cap);
+    if (h->R == 32)
+        sri::generic_kernel<32, SOLVE><<<grid, 128, h->generic_smem, h->stream>>>(p);
+    else
+        sri::generic_kernel<64, SOLVE><<<grid, 256, h->generic_smem, h->stream>>>(p);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+template <bool SOLVE>
 int launch_fused16(sri_context* h, const sri::FusedParams& p) {
     if (p.batch <= 0) return SRI_OK;
+    if (h->R != 0) return launch_generic<SOLVE>(h, p);
     const long long pairs = (p.batch + 1) / 2;
     const long long want = (pairs + (kFusedThreads / 32) - 1) / (kFusedThreads / 32);
     const int per_sm = SOLVE ? h->fused_blocks_per_sm : h->stage_blocks_per_sm;
@@ -320,7 +338,6 @@ int sri_create(int N, int device, sri_handle* out) {
     if (!out) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create: out == NULL");
     *out = nullptr;
     if (N < 2 || N > 64) return fail(SRI_ERR_UNSUPPORTED_N, "sri_create: N must be in [2, 64]");
-    if (N > 16) return fail(SRI_ERR_UNSUPPORTED_N, "sri_create: N > 16 not built yet in this revision");
     int ndev = 0;
     SRI_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(SRI_ERR_CUDA, "sri_create: no such CUDA device (there is no CPU fallback)");
@@ -336,7 +353,7 @@ int sri_create(int N, int device, sri_handle* out) {
     h->stream = h->own_stream;
 
     const int M = h->M;
-    {
+    if (N <= 16) {
         using L = sri::OpsLayout16;
         std::vector<double> t(L::total, 0.0);
         for (int j = 0; j < M; ++j)
@@ -353,6 +370,33 @@ int sri_create(int N, int device, sri_handle* out) {
         }
         SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * L::total));
         SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * L::total, cudaMemcpyHostToDevice));
+    } else {
+        h->R = (M <= 32) ? 32 : 64;
+        const sri::OpsLayoutGeneric L{h->R};
+        std::vector<double> t(L.total(), 0.0);
+        for (int j = 0; j < M; ++j)
+            for (int i = 0; i < M; ++i) {
+                t[L.Sp() + j * h->R + i] = h->ops.S[j * M + i];
+                t[L.STt() + j * h->R + i] = h->ops.ST[j * M + i];
+            }
+        for (int i = 0; i < M; ++i) {
+            t[L.g() + i] = h->ops.g[i];
+            t[L.gT() + i] = h->ops.gT[i];
+            t[L.DTI() + i] = h->ops.D_TI[i];
+        }
+        SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * L.total()));
+        SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * L.total(), cudaMemcpyHostToDevice));
+        h->generic_smem = sri::generic_smem_doubles(M, h->R) * sizeof(double);
+        if (h->R == 32) {
+            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::generic_kernel<32, true>, 128, h->generic_smem));
+        } else {
+            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::generic_kernel<64, true>, 256, h->generic_smem));
+        }
+        if (h->generic_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: generic kernel does not fit on this device"); }
     }
     {
         std::vector<double> t(N);
@@ -361,7 +405,9 @@ int sri_create(int N, int device, sri_handle* out) {
         SRI_CUDA(cudaMemcpy(h->d_tnodes, t.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
     }
     SRI_CUDA(cudaMalloc(&h->d_reduce, sizeof(double) * 2));
-    if (M == 15) {
+    if (N > 16) {
+        h->fused_blocks_per_sm = h->stage_blocks_per_sm = h->generic_blocks_per_sm;
+    } else if (M == 15) {
         SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_blocks_per_sm, sri::fused16_kernel<15, true>, kFusedThreads, kFusedSmem));
         SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->stage_blocks_per_sm, sri::fused16_kernel<15, false>, kFusedThreads, kFusedSmem));
     } else {

@@ -169,3 +169,30 @@ def test_shape_residual(h16, oracle16, torch_mod):
     red = red.cpu().numpy()
     assert abs(red[0] - (rho_ref ** 2).sum()) <= 1e-11 * (rho_ref ** 2).sum()
     assert red[1] == np.abs(rho_ref).max() or abs(red[1] - np.abs(rho_ref).max()) <= 1e-12 * red[1]
+
+
+@pytest.mark.parametrize("N,batch", [(17, 129), (24, 100), (32, 200), (33, 65), (48, 40), (64, 48)])
+def test_high_resolution_node_counts(sri_lib, make_oracle, torch_mod, N, batch):
+    """BASELINE configs[3]: N = 32 and N = 64 (and sizes in between) through the shared-memory resident kernel."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    o = make_oracle(N)
+    rng = np.random.default_rng(N)
+    K, F, Mt, fb = o.generate_rods(77, 0, batch)
+    q0 = rng.normal(size=(batch, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    r0 = rng.normal(size=(batch, 3))
+    lbar = rng.normal(size=(batch, 3, N))
+    ref = o.integrate_all(K, F, Mt, q0=q0, r0=r0, fbar=fb, lbar=lbar)
+    with SpectralRodIntegrator(N, 0) as h:
+        got = _gpu_all(h, torch_mod, K, F, Mt, q0=q0, r0=r0, fbar=fb, lbar=lbar)
+        assert (got["info"] == 0).all()
+        for s in "Qrnm":
+            assert rel_err(got[s], ref[s]) <= TOL, (N, s, rel_err(got[s], ref[s]))
+        # separate-stage entry points on the same handle
+        t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+        Q = h.integrate_quaternions(t(K), q0=t(q0))
+        r = h.integrate_position(Q, r0=t(r0))
+        n = h.integrate_stress(t(F), fbar=t(fb))
+        m = h.integrate_couple(Q, n, t(Mt), q0=t(q0), lbar=t(lbar))
+        h.synchronize()
+        for name, val in (("Q", Q), ("r", r), ("n", n), ("m", m)):
+            assert rel_err(val.cpu().numpy(), ref[name]) <= TOL, (N, name)
