@@ -536,3 +536,9 @@ void sri_oracle_generate_rods(int N, uint64_t seed, long first_rod, long batch, 
     }
     free(x);
 }
+
+/* raw Philox block for the known-answer test in tests/ */
+void sri_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}

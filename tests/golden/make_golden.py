@@ -1,0 +1,47 @@
+"""Regenerates the committed golden fixtures.  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+reference_main_default.json  -- output of the reference's own main() (compiled verbatim against oracle/eigen_shim),
+                                at its native 6 significant digits and at 17.
+oracle_default_stages34.json -- stages 3-4 for the same rod (F_tip=(0,0,-1), M_tip=0); the reference does not
+                                implement them, so this file is produced by the oracle and pinned by the analytic
+                                known-answer tests in tests/test_oracle_cpu.py.
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from oracle.build_reference import run_reference  # noqa: E402
+from oracle.oracle import Oracle, build_oracle  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+QE = [0, 0, 0, 1.2877691307032, -1.63807499160786, 0.437406679142598, 0, 0, 0]
+
+full = run_reference(17)
+native = run_reference(None)
+(HERE / "reference_main_default.json").write_text(json.dumps({
+    "source": "/root/reference/main.cpp compiled verbatim against oracle/eigen_shim; qe of main.cpp:187-195; N=16",
+    "qe": QE,
+    "stdout_native_precision": native["stdout"],
+    "Q_stack": [repr(float(v)) for v in full["Q_stack"]],
+    "r_stack_rows": [[repr(float(v)) for v in row] for row in full["r_stack"]],
+}, indent=1))
+
+build_oracle()
+o = Oracle(16)
+K = o.strain_from_modes(np.array(QE, dtype=np.float64))
+F = np.array([[0.0, 0.0, -1.0]]); Mt = np.zeros((1, 3))
+out = o.integrate_all(K, F, Mt)
+(HERE / "oracle_default_stages34.json").write_text(json.dumps({
+    "source": "oracle/sri_oracle.c (SURVEY Appendix A.4-A.5); qe of main.cpp:187-195; F_tip=(0,0,-1), M_tip=0; N=16",
+    "K": [[repr(float(v)) for v in row] for row in K[0]],
+    "n": [[repr(float(v)) for v in row] for row in out["n"][0]],
+    "m": [[repr(float(v)) for v in row] for row in out["m"][0]],
+}, indent=1))
+print("golden fixtures written to", HERE)
