@@ -46,6 +46,12 @@ struct sri_context {
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     int fused_blocks_per_sm = 0;
     int stage_blocks_per_sm = 0;
+    // host-buffer pipeline: chunks of rods flow H2D -> kernel -> D2H on rotating streams with persistent staging
+    static constexpr int kPipeSlots = 3;
+    static constexpr int kPipeArrays = 13;
+    cudaStream_t pipe_stream[kPipeSlots] = {nullptr, nullptr, nullptr};
+    void* pipe_buf[kPipeSlots][kPipeArrays] = {};
+    size_t pipe_cap[kPipeSlots][kPipeArrays] = {};
 };
 
 namespace {
@@ -256,33 +262,106 @@ constexpr int kFusedThreads = 128;
 constexpr size_t kFusedSmem = (sri::OpsLayout16::total + (kFusedThreads / 32) * sri::kWarpScratch16) * sizeof(double);
 
 template <bool SOLVE>
-int launch_generic(sri_context* h, const sri::FusedParams& p) {
+int launch_generic(sri_context* h, const sri::FusedParams& p, cudaStream_t stream) {
     const long long cap = (long long)h->sm_count * h->generic_blocks_per_sm;
     const int grid = (int)(p.batch < cap ? p.batch : cap);
     if (h->R == 32)
-        sri::generic_kernel<32, SOLVE><<<grid, 128, h->generic_smem, h->stream>>>(p);
+        sri::generic_kernel<32, SOLVE><<<grid, 128, h->generic_smem, stream>>>(p);
     else
-        sri::generic_kernel<64, SOLVE><<<grid, 256, h->generic_smem, h->stream>>>(p);
+        sri::generic_kernel<64, SOLVE><<<grid, 256, h->generic_smem, stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return SRI_OK;
 }
 
 template <bool SOLVE>
-int launch_fused16(sri_context* h, const sri::FusedParams& p) {
+int launch_fused16(sri_context* h, const sri::FusedParams& p, cudaStream_t stream = nullptr, bool use_handle_stream = true) {
     if (p.batch <= 0) return SRI_OK;
-    if (h->R != 0) return launch_generic<SOLVE>(h, p);
+    if (use_handle_stream) stream = h->stream;
+    if (h->R != 0) return launch_generic<SOLVE>(h, p, stream);
     const long long pairs = (p.batch + 1) / 2;
     const long long want = (pairs + (kFusedThreads / 32) - 1) / (kFusedThreads / 32);
     const int per_sm = SOLVE ? h->fused_blocks_per_sm : h->stage_blocks_per_sm;
     const long long cap = (long long)h->sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
     if (h->M == 15)
-        sri::fused16_kernel<15, SOLVE><<<grid, kFusedThreads, kFusedSmem, h->stream>>>(p);
+        sri::fused16_kernel<15, SOLVE><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
     else
-        sri::fused16_kernel<0, SOLVE><<<grid, kFusedThreads, kFusedSmem, h->stream>>>(p);
+        sri::fused16_kernel<0, SOLVE><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+// ---- host-buffer pipeline --------------------------------------------------------------------------------------
+
+bool all_host_pointers(const sri_rod_batch* r) {
+    const void* ptrs[] = {r->K, r->q0, r->r0, r->Gamma, r->fbar, r->lbar, r->F_tip, r->M_tip, r->Q, r->r, r->n, r->m, r->info};
+    for (const void* p : ptrs)
+        if (p && is_device_pointer(p)) return false;
+    return true;
+}
+
+int pipe_reserve(sri_context* h, int slot, int arr, size_t bytes, void** out) {
+    if (h->pipe_cap[slot][arr] < bytes) {
+        if (h->pipe_buf[slot][arr]) SRI_CUDA(cudaFree(h->pipe_buf[slot][arr]));
+        h->pipe_buf[slot][arr] = nullptr;
+        h->pipe_cap[slot][arr] = 0;
+        SRI_CUDA(cudaMalloc(&h->pipe_buf[slot][arr], bytes));
+        h->pipe_cap[slot][arr] = bytes;
+    }
+    *out = h->pipe_buf[slot][arr];
+    return SRI_OK;
+}
+
+// All buffers live on the host: split the batch into chunks and overlap the H2D copy of chunk c+1, the kernel of
+// chunk c and the D2H copy of chunk c-1 on three streams (pinned host memory makes the copies truly asynchronous;
+// pageable memory still works, serialised by the driver).  Returns after every result has landed.
+int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
+    const int N = h->N, M = h->M;
+    const int64_t B = r->batch;
+    const int64_t chunk = (N <= 16) ? 32768 : (N <= 32 ? 8192 : 2048);
+    for (int sl = 0; sl < sri_context::kPipeSlots; ++sl)
+        if (!h->pipe_stream[sl]) SRI_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[sl], cudaStreamNonBlocking));
+    struct Arr { const void* src; void* dst; size_t per_rod; };
+    int c = 0;
+    for (int64_t first = 0; first < B; first += chunk, ++c) {
+        const int slot = c % sri_context::kPipeSlots;
+        cudaStream_t st = h->pipe_stream[slot];
+        const int64_t nb = (B - first < chunk) ? (B - first) : chunk;
+        const Arr ins[8] = {{r->K, nullptr, (size_t)3 * N * 8}, {r->q0, nullptr, 32}, {r->r0, nullptr, 24},
+                            {r->Gamma, nullptr, (size_t)3 * N * 8}, {r->fbar, nullptr, (size_t)3 * N * 8},
+                            {r->lbar, nullptr, (size_t)3 * N * 8}, {r->F_tip, nullptr, 24}, {r->M_tip, nullptr, 24}};
+        const Arr outs[5] = {{nullptr, r->Q, (size_t)4 * M * 8}, {nullptr, r->r, (size_t)3 * M * 8}, {nullptr, r->n, (size_t)3 * M * 8},
+                             {nullptr, r->m, (size_t)3 * M * 8}, {nullptr, r->info, 4}};
+        void* din[8] = {};
+        void* dout[5] = {};
+        for (int a = 0; a < 8; ++a) {
+            if (!ins[a].src) continue;
+            SRI_TRY(pipe_reserve(h, slot, a, (size_t)chunk * ins[a].per_rod, &din[a]));
+            SRI_CUDA(cudaMemcpyAsync(din[a], static_cast<const char*>(ins[a].src) + (size_t)first * ins[a].per_rod,
+                                     (size_t)nb * ins[a].per_rod, cudaMemcpyHostToDevice, st));
+        }
+        for (int a = 0; a < 5; ++a) {
+            if (!outs[a].dst) continue;
+            SRI_TRY(pipe_reserve(h, slot, 8 + a, (size_t)chunk * outs[a].per_rod, &dout[a]));
+        }
+        sri::FusedParams p{};
+        p.batch = nb; p.N = N; p.M = M; p.ops = h->d_ops16;
+        p.K = static_cast<const double*>(din[0]); p.q0 = static_cast<const double*>(din[1]);
+        p.r0 = static_cast<const double*>(din[2]); p.Gamma = static_cast<const double*>(din[3]);
+        p.fbar = static_cast<const double*>(din[4]); p.lbar = static_cast<const double*>(din[5]);
+        p.F_tip = static_cast<const double*>(din[6]); p.M_tip = static_cast<const double*>(din[7]);
+        p.Q = static_cast<double*>(dout[0]); p.r = static_cast<double*>(dout[1]); p.n = static_cast<double*>(dout[2]);
+        p.m = static_cast<double*>(dout[3]); p.info = static_cast<int*>(dout[4]);
+        SRI_TRY(launch_fused16<true>(h, p, st, false));
+        for (int a = 0; a < 5; ++a) {
+            if (!outs[a].dst) continue;
+            SRI_CUDA(cudaMemcpyAsync(static_cast<char*>(outs[a].dst) + (size_t)first * outs[a].per_rod, dout[a],
+                                     (size_t)nb * outs[a].per_rod, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) SRI_CUDA(cudaStreamSynchronize(h->pipe_stream[sl]));
     return SRI_OK;
 }
 
@@ -425,6 +504,11 @@ int sri_destroy(sri_handle h) {
     if (h->d_ops16) cudaFree(h->d_ops16);
     if (h->d_tnodes) cudaFree(h->d_tnodes);
     if (h->d_reduce) cudaFree(h->d_reduce);
+    for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) {
+        for (int a = 0; a < sri_context::kPipeArrays; ++a)
+            if (h->pipe_buf[sl][a]) cudaFree(h->pipe_buf[sl][a]);
+        if (h->pipe_stream[sl]) cudaStreamDestroy(h->pipe_stream[sl]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return SRI_OK;
@@ -496,6 +580,7 @@ int sri_integrate_all(sri_handle h, const sri_rod_batch* rods) {
     if ((rods->n || rods->m) && !rods->F_tip) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: F_tip is required for n/m");
     if (rods->m && !rods->M_tip) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: M_tip is required for m");
     const int N = h->N, M = h->M;
+    if (all_host_pointers(rods)) return integrate_all_host_pipeline(h, rods);
     Staging st(h);
     sri::FusedParams p{};
     p.batch = B; p.N = N; p.M = M; p.ops = h->d_ops16;

@@ -1,0 +1,150 @@
+// sri_reference_api.hpp -- the reference's C++ function surface on top of the C ABI (include/sri.h).
+//
+// A maintainer of aGotelli/experimental_gpu_programming_for_a_spectral_numerical_integration keeps calling
+//   ComputeChebyshevPoints<N>(), GetCoefficients_c<N>(), getDn<N>(), Phi<na,ne>(X), integrateQuaternions(),
+//   updatePositionb(Q_stack), integratePosition()
+// exactly as main.cpp does, but links libsri_cuda.so instead of compiling the Eigen code.  Differences, all forced by
+// the absence of Eigen in the boundary: dense results come back as sri::ref::Matrix (column-major, Eigen's default
+// storage order, with operator()(i,j) and data()), and the global `qe` of main.cpp:17 is an explicit argument.
+// Batched entry points (the reason to use a GPU at all) are the C functions of sri.h; this header is the
+// single-rod compatibility layer.
+//
+// Header-only, C++17, depends only on sri.h.  Errors surface as std::runtime_error carrying sri_last_error_string().
+#ifndef SRI_REFERENCE_API_HPP
+#define SRI_REFERENCE_API_HPP
+
+#include <array>
+#include <cstddef>
+#include <memory>
+#include <ostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sri.h"
+
+namespace sri {
+namespace ref {
+
+inline void check(int status, const char* where) {
+    if (status != SRI_OK) throw std::runtime_error(std::string(where) + ": " + sri_last_error_string());
+}
+
+// Column-major dense matrix of double (what Eigen::MatrixXd is at the boundary).
+class Matrix {
+public:
+    Matrix() = default;
+    Matrix(int rows, int cols) : r_(rows), c_(cols), d_(static_cast<std::size_t>(rows) * cols, 0.0) {}
+    int rows() const { return r_; }
+    int cols() const { return c_; }
+    int size() const { return r_ * c_; }
+    double& operator()(int i, int j) { return d_[static_cast<std::size_t>(j) * r_ + i]; }
+    double operator()(int i, int j) const { return d_[static_cast<std::size_t>(j) * r_ + i]; }
+    double& operator()(int i) { return d_[i]; }
+    double operator()(int i) const { return d_[i]; }
+    double* data() { return d_.data(); }
+    const double* data() const { return d_.data(); }
+
+private:
+    int r_ = 0, c_ = 0;
+    std::vector<double> d_;
+};
+
+inline std::ostream& operator<<(std::ostream& os, const Matrix& m) {
+    for (int i = 0; i < m.rows(); ++i) {
+        if (i) os << "\n";
+        for (int j = 0; j < m.cols(); ++j) os << (j ? " " : "") << m(i, j);
+    }
+    return os;
+}
+
+// RAII handle: one cached operator set per (N, device).
+class Handle {
+public:
+    explicit Handle(int N, int device = 0) { check(sri_create(N, device, &h_), "sri_create"); }
+    ~Handle() { sri_destroy(h_); }
+    Handle(const Handle&) = delete;
+    Handle& operator=(const Handle&) = delete;
+    sri_handle get() const { return h_; }
+
+private:
+    sri_handle h_ = nullptr;
+};
+
+}  // namespace ref
+}  // namespace sri
+
+// ---- include/chebyshev_differentiation.h:19-30 ------------------------------------------------------------------
+template <unsigned int t_number_of_chebyshev_nodes, unsigned int t_L = 1>
+static std::array<double, t_number_of_chebyshev_nodes> ComputeChebyshevPoints() {
+    std::array<double, t_number_of_chebyshev_nodes> x;
+    sri::ref::check(sri_chebyshev_points(t_number_of_chebyshev_nodes, static_cast<double>(t_L), x.data()), "sri_chebyshev_points");
+    return x;
+}
+
+// ---- include/chebyshev_differentiation.h:37-52 ------------------------------------------------------------------
+template <unsigned int t_number_of_chebyshev_nodes>
+static std::array<double, t_number_of_chebyshev_nodes> GetCoefficients_c() {
+    std::array<double, t_number_of_chebyshev_nodes> c;
+    sri::ref::check(sri_chebyshev_coefficients(t_number_of_chebyshev_nodes, c.data()), "sri_chebyshev_coefficients");
+    return c;
+}
+
+// ---- include/chebyshev_differentiation.h:59-108 -----------------------------------------------------------------
+template <unsigned int t_number_of_chebyshev_nodes>
+static sri::ref::Matrix getDn() {
+    sri::ref::Matrix Dn(t_number_of_chebyshev_nodes, t_number_of_chebyshev_nodes);
+    sri::ref::check(sri_chebyshev_dn(t_number_of_chebyshev_nodes, Dn.data()), "sri_chebyshev_dn");
+    return Dn;
+}
+
+// ---- include/utilities.h:49-67 ------------------------------------------------------------------------------------
+template <unsigned int t_na, unsigned int t_ne>
+static const sri::ref::Matrix Phi(const double t_X, const double& t_begin = 0, const double& t_end = 1) {
+    sri::ref::Matrix P(t_na, t_na * t_ne);
+    sri::ref::check(sri_phi(t_na, t_ne, t_X, t_begin, t_end, P.data()), "sri_phi");
+    return P;
+}
+
+// ---- main.cpp:91-118 (the global qe of main.cpp:17 becomes the argument) ----------------------------------------
+template <unsigned int t_number_of_chebyshev_nodes = 16, unsigned int t_ne = 3>
+static sri::ref::Matrix integrateQuaternions(const std::array<double, 3 * t_ne>& qe, int device = 0) {
+    constexpr int N = t_number_of_chebyshev_nodes, M = N - 1;
+    sri::ref::Handle h(N, device);
+    std::vector<double> K(3 * N);
+    sri::ref::check(sri_strain_from_modes(h.get(), 1, t_ne, qe.data(), K.data()), "sri_strain_from_modes");
+    sri::ref::Matrix Q_stack(4 * M, 1);
+    int info = 0;
+    sri::ref::check(sri_integrate_quaternions(h.get(), 1, K.data(), nullptr, Q_stack.data(), &info), "sri_integrate_quaternions");
+    return Q_stack;
+}
+
+// ---- main.cpp:121-140: b.row(i) = (R(q_i) (1,0,0))^T; kept for callers that want the stage-2 right-hand side ----
+template <unsigned int t_number_of_chebyshev_nodes = 16>
+static sri::ref::Matrix updatePositionb(const sri::ref::Matrix& t_Q_stack) {
+    constexpr int M = t_number_of_chebyshev_nodes - 1;
+    sri::ref::Matrix b(M, 3);
+    for (int i = 0; i < M; ++i) {
+        const double w = t_Q_stack(i), x = t_Q_stack(i + M), y = t_Q_stack(i + 2 * M), z = t_Q_stack(i + 3 * M);
+        b(i, 0) = 1 - (2 * y * y + 2 * z * z);
+        b(i, 1) = 2 * y * x + 2 * z * w;
+        b(i, 2) = 2 * z * x - 2 * y * w;
+    }
+    return b;
+}
+
+// ---- main.cpp:145-176 (without the redundant second quaternion solve of main.cpp:147) ---------------------------
+template <unsigned int t_number_of_chebyshev_nodes = 16, unsigned int t_ne = 3>
+static sri::ref::Matrix integratePosition(const std::array<double, 3 * t_ne>& qe, int device = 0) {
+    constexpr int N = t_number_of_chebyshev_nodes, M = N - 1;
+    sri::ref::Handle h(N, device);
+    std::vector<double> K(3 * N);
+    sri::ref::check(sri_strain_from_modes(h.get(), 1, t_ne, qe.data(), K.data()), "sri_strain_from_modes");
+    sri::ref::Matrix r_stack(M, 3);  // column-major (N-1) x 3 == the ABI's [3][M] layout
+    sri_rod_batch rb{};
+    rb.batch = 1; rb.K = K.data(); rb.r = r_stack.data();
+    sri::ref::check(sri_integrate_all(h.get(), &rb), "sri_integrate_all");
+    return r_stack;
+}
+
+#endif  // SRI_REFERENCE_API_HPP

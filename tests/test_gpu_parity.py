@@ -196,3 +196,41 @@ def test_high_resolution_node_counts(sri_lib, make_oracle, torch_mod, N, batch):
         h.synchronize()
         for name, val in (("Q", Q), ("r", r), ("n", n), ("m", m)):
             assert rel_err(val.cpu().numpy(), ref[name]) <= TOL, (N, name)
+
+
+def test_cpp_dropin_reproduces_reference_main(sri_lib):
+    """examples/reference_main.cpp = the reference's main() written against include/sri_reference_api.hpp (C++ host
+    code -> C ABI -> CUDA).  Its dumps must agree with the golden dumps of the real reference main()."""
+    import json
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "examples" / "reference_main_gpu"
+    if not exe.exists():
+        import __graft_entry__ as g
+        g._build_cpp_example(root / "experimental_gpu_programming_for_a_spectral_numerical_integration_b200" / "libsri_cuda.so")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    gold = json.loads((root / "tests" / "golden" / "reference_main_default.json").read_text())
+    head, tail = out.split("r_stack : \n")
+    Q = np.array([float(v) for v in head.split("\n", 1)[1].split()])
+    r = np.array([[float(v) for v in line.split()] for line in tail.strip().split("\n")])
+    assert head.startswith("Q_stack : \n")
+    assert np.abs(Q - np.array([float(v) for v in gold["Q_stack"]])).max() < 5e-6      # printed at 6 significant digits
+    assert np.abs(r - np.array([[float(v) for v in row] for row in gold["r_stack_rows"]])).max() < 5e-6
+
+
+def test_host_pipeline_multi_chunk_is_bit_identical_to_device_path(h16, oracle16, torch_mod):
+    """Host buffers larger than one pipeline chunk (32768 rods): chunked H2D/kernel/D2H must reproduce the
+    device-resident call bit for bit, including the ragged last chunk."""
+    B = 2 * 32768 + 4097
+    K, F, Mt, fb = oracle16.generate_rods(0x5EED, 10 ** 9, B)
+    dev = _gpu_all(h16, torch_mod, K, F, Mt, fbar=fb)
+    info = np.full(B, -1, dtype=np.int32)
+    host = h16.integrate_all(K, F, Mt, fbar=fb, info=info)
+    assert (info == 0).all()
+    for s in "Qrnm":
+        assert np.array_equal(host[s], dev[s]), s
+    pinned = {k: torch_mod.from_numpy(v).pin_memory() for k, v in (("K", K), ("F", F), ("M", Mt), ("fb", fb))}
+    outp = h16.integrate_all(pinned["K"], pinned["F"], pinned["M"], fbar=pinned["fb"],
+                             Q=torch_mod.empty((B, 4, 15), dtype=torch_mod.float64).pin_memory(), want=("Q", "m"))
+    assert np.array_equal(outp["Q"].numpy(), dev["Q"]) and np.array_equal(outp["m"].numpy(), dev["m"])
