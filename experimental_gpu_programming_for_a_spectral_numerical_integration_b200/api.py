@@ -244,6 +244,25 @@ class SpectralRodIntegrator:
         )
         return rho
 
+    def project_onto_modes(self, f, ne: int, out=None):
+        """Nodal field f [batch][3][N] -> modal coordinates [batch][3*ne] (Clenshaw-Curtis Galerkin projection)."""
+        self._follow_torch(f)
+        batch = f.shape[0]
+        if out is None:
+            out = _empty_like_kind(f, (batch, 3 * ne))
+        _lib.check(self._lib.sri_project_onto_modes(self._h, batch, int(ne), _ptr(f, "f"), _ptr(out, "out")), "sri_project_onto_modes")
+        return out
+
+    def solve_small_batched(self, A, b, out=None, info=None):
+        """A [batch][n][n] (row-major, destroyed), b [batch][n] -> x [batch][n]; CUDA tensors only."""
+        self._follow_torch(A)
+        batch, n = b.shape
+        if out is None:
+            out = _empty_like_kind(b, (batch, n))
+        _lib.check(self._lib.sri_solve_small_batched(self._h, batch, n, _ptr(A, "A"), _ptr(b, "b"), _ptr(out, "x"),
+                                                     _ptr(info, "info", np.int32)), "sri_solve_small_batched")
+        return out
+
     def generate_rods(self, seed: int, first_rod: int, batch: int, K=None, F_tip=None, M_tip=None, fbar=None):
         self._follow_torch(K, F_tip, M_tip, fbar)
         _lib.check(

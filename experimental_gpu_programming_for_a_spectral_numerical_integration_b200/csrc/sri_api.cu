@@ -44,6 +44,7 @@ struct sri_context {
     int generic_blocks_per_sm = 0;
     double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
+    double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
     int fused_blocks_per_sm = 0;
     int stage_blocks_per_sm = 0;
     // host-buffer pipeline: chunks of rods flow H2D -> kernel -> D2H on rotating streams with persistent staging
@@ -203,6 +204,63 @@ __global__ void shape_residual_kernel(long long batch, int N, const double* __re
             }
         }
     }
+}
+
+// out[b][c*ne+k] = sum_i w_i P_k(t_i) f[b][c][i]: one thread per (rod, component), Legendre recurrence per node.
+__global__ void project_onto_modes_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
+                                          const double* __restrict__ ccw, const double* __restrict__ f,
+                                          double* __restrict__ out) {
+    const long long bc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bc >= batch * 3) return;
+    double acc[8];
+    for (int k = 0; k < ne; ++k) acc[k] = 0.0;
+    const double* fi = f + bc * N;
+    for (int i = 0; i < N; ++i) {
+        const double t = tnodes[i], wf = ccw[i] * fi[i];
+        double pm = 1.0, p = t;
+        acc[0] = fma(wf, 1.0, acc[0]);
+        if (ne > 1) acc[1] = fma(wf, p, acc[1]);
+        for (int k = 1; k + 1 < ne; ++k) {
+            const double pn = ((2 * k + 1) * t * p - k * pm) / (k + 1);
+            pm = p; p = pn;
+            acc[k + 1] = fma(wf, p, acc[k + 1]);
+        }
+    }
+    for (int k = 0; k < ne; ++k) out[bc * ne + k] = acc[k];
+}
+
+// One thread per system: Gaussian elimination with partial pivoting, in place in global memory (row-major A).
+__global__ void solve_small_kernel(long long batch, int n, double* __restrict__ A, const double* __restrict__ b,
+                                   double* __restrict__ x, int* __restrict__ info) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= batch) return;
+    double* a = A + s * n * n;
+    double rhs[24];
+    for (int i = 0; i < n; ++i) rhs[i] = b[s * n + i];
+    int bad = 0;
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        double best = fabs(a[k * n + k]);
+        for (int i = k + 1; i < n; ++i) { const double v = fabs(a[i * n + k]); if (v > best) { best = v; p = i; } }
+        if (best == 0.0) { if (!bad) bad = k + 1; continue; }
+        if (p != k) {
+            for (int j = k; j < n; ++j) { const double t = a[k * n + j]; a[k * n + j] = a[p * n + j]; a[p * n + j] = t; }
+            const double t = rhs[k]; rhs[k] = rhs[p]; rhs[p] = t;
+        }
+        const double inv = 1.0 / a[k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            const double l = a[i * n + k] * inv;
+            for (int j = k + 1; j < n; ++j) a[i * n + j] = fma(-l, a[k * n + j], a[i * n + j]);
+            rhs[i] = fma(-l, rhs[k], rhs[i]);
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        double v = rhs[k];
+        for (int j = k + 1; j < n; ++j) v = fma(-a[k * n + j], rhs[j], v);
+        rhs[k] = v / a[k * n + k];
+    }
+    for (int i = 0; i < n; ++i) x[s * n + i] = rhs[i];
+    if (info) info[s] = bad;
 }
 
 // SURVEY 8(d) synthetic rods.  One thread per rod.
@@ -484,6 +542,12 @@ int sri_create(int N, int device, sri_handle* out) {
         SRI_CUDA(cudaMemcpy(h->d_tnodes, t.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
     }
     SRI_CUDA(cudaMalloc(&h->d_reduce, sizeof(double) * 2));
+    {
+        std::vector<double> w(N);
+        sri_host::clenshaw_curtis_weights(N, w.data());
+        SRI_CUDA(cudaMalloc(&h->d_ccw, sizeof(double) * N));
+        SRI_CUDA(cudaMemcpy(h->d_ccw, w.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+    }
     if (N > 16) {
         h->fused_blocks_per_sm = h->stage_blocks_per_sm = h->generic_blocks_per_sm;
     } else if (M == 15) {
@@ -504,6 +568,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_ops16) cudaFree(h->d_ops16);
     if (h->d_tnodes) cudaFree(h->d_tnodes);
     if (h->d_reduce) cudaFree(h->d_reduce);
+    if (h->d_ccw) cudaFree(h->d_ccw);
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) {
         for (int a = 0; a < sri_context::kPipeArrays; ++a)
             if (h->pipe_buf[sl][a]) cudaFree(h->pipe_buf[sl][a]);
@@ -688,6 +753,33 @@ int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const doubl
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();
+}
+
+int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f, double* out) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!f || !out))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_project_onto_modes: bad arguments (1 <= ne <= 8)");
+    if (batch == 0) return SRI_OK;
+    Staging st(h);
+    const double* df; double* dout;
+    SRI_TRY(st.in(f, (size_t)batch * 3 * h->N, &df));
+    SRI_TRY(st.out(out, (size_t)batch * 3 * ne, &dout));
+    const long long total = (long long)batch * 3;
+    project_onto_modes_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, h->d_ccw, df, dout);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const double* b, double* x, int* info) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || n < 1 || n > 24 || (batch > 0 && (!A || !b || !x))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: bad arguments (1 <= n <= 24)");
+    if (batch == 0) return SRI_OK;
+    for (const void* p : {(const void*)A, (const void*)b, (const void*)x, (const void*)info})
+        if (p && !is_device_pointer(p)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: device pointers only");
+    solve_small_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(batch, n, A, b, x, info);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
 }
 
 int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t batch, double* K, double* F_tip,

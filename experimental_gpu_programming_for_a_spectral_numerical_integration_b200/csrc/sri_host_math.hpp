@@ -73,6 +73,21 @@ inline bool invert_extended(int n, const double* A, double* Ainv) {
     return true;
 }
 
+// Clenshaw-Curtis weights of the N Chebyshev-Gauss-Lobatto nodes x_j = (1 + cos(pi j/(N-1)))/2 on [0,1]
+// (exact for polynomials of degree <= N-1).
+inline void clenshaw_curtis_weights(int N, double* w) {
+    const int n = N - 1;
+    for (int j = 0; j <= n; ++j) {
+        long double s = 0.0L;
+        for (int k = 0; k <= n / 2; ++k) {
+            const long double bk = (k == 0 || 2 * k == n) ? 1.0L : 2.0L;
+            s += bk / (1.0L - 4.0L * k * k) * cosl(2.0L * k * j * M_PIl / n);
+        }
+        const long double cj = (j == 0 || j == n) ? 1.0L : 2.0L;
+        w[j] = static_cast<double>(0.5L * cj / n * s);  // 0.5: interval [0,1] instead of [-1,1]
+    }
+}
+
 struct OperatorSet {
     int N = 0, M = 0;
     std::vector<double> x;      // nodes

@@ -136,6 +136,16 @@ int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const doubl
                        const double* Q, const double* q0, const double* m, const double* M_tip, double* rho,
                        double* norm2_and_max);
 
+/* Galerkin projection of a nodal field onto the Legendre strain modes (rod_modeling.pdf eqs. 2.14, 2.16; the
+ * transpose of Phi, include/utilities.h:49-67): out[b][c*ne+k] = sum_i w_i P_k(2 x_i - 1) f[b][c][i], with w the
+ * Clenshaw-Curtis weights of the N Chebyshev nodes on [0,1].  f [batch][3][N] -> out [batch][3*ne]. */
+int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f, double* out);
+
+/* Batched dense solve A x = b for small systems (n <= 24), partial pivoting, one rod per thread: the Newton step
+ * of the static shape problem.  A [batch][n][n] row-major (destroyed), b [batch][n] -> x [batch][n].
+ * info [batch] or NULL as in sri_integrate_quaternions.  Device pointers only. */
+int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const double* b, double* x, int* info);
+
 /* ---- synthetic inputs of SURVEY 8(d): counter-based, identical for any sharding ------------------------ */
 
 /* Fills K, F_tip, M_tip, fbar for rods [first_rod, first_rod+batch): K_c(X) = alpha + beta (2X-1) with
