@@ -11,6 +11,7 @@
 
 #include "sri_fused16.cuh"
 #include "sri_generic.cuh"
+#include "sri_stage_dmma.cuh"
 #include "sri_host_math.hpp"
 
 namespace {
@@ -423,6 +424,19 @@ int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
     return SRI_OK;
 }
 
+template <int STAGE>
+int launch_stage_dmma(sri_context* h, const sri::FusedParams& p) {
+    if (p.batch <= 0) return SRI_OK;
+    const long long tiles = (p.batch + 7) / 8;
+    const long long want = (tiles + 3) / 4;
+    const long long cap = (long long)h->sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    sri::stage_dmma_kernel<STAGE><<<grid, 128, 0, h->stream>>>(p);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
 int check_handle(sri_handle h) {
     if (!h) return fail(SRI_ERR_INVALID_ARGUMENT, "null handle");
     cudaError_t e = cudaSetDevice(h->device);
@@ -492,7 +506,12 @@ int sri_create(int N, int device, sri_handle* out) {
     const int M = h->M;
     if (N <= 16) {
         using L = sri::OpsLayout16;
-        std::vector<double> t(L::total, 0.0);
+        std::vector<double> t(sri::StageTables::total, 0.0);
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) {
+                t[sri::StageTables::Srm + i * 16 + j] = h->ops.S[j * M + i];
+                t[sri::StageTables::STrm + i * 16 + j] = h->ops.ST[j * M + i];
+            }
         for (int j = 0; j < M; ++j)
             for (int i = 0; i < M; ++i) {
                 t[L::St + j * sri::MP16 + i] = -0.5 * h->ops.S[j * M + i];
@@ -505,8 +524,8 @@ int sri_create(int N, int device, sri_handle* out) {
             t[L::DTI + i] = h->ops.D_TI[i];
             t[L::DnIN + i] = h->ops.Dn_IN[i];
         }
-        SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * L::total));
-        SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * L::total, cudaMemcpyHostToDevice));
+        SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * sri::StageTables::total));
+        SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * sri::StageTables::total, cudaMemcpyHostToDevice));
     } else {
         h->R = (M <= 32) ? 32 : 64;
         const sri::OpsLayoutGeneric L{h->R};
@@ -685,7 +704,8 @@ int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const d
     SRI_TRY(st.in(Gamma, (size_t)batch * 3 * N, &p.Gamma));
     SRI_TRY(st.in(r0, (size_t)batch * 3, &p.r0));
     SRI_TRY(st.out(r, (size_t)batch * 3 * M, &p.r));
-    SRI_TRY(launch_fused16<false>(h, p));
+    if (h->R == 0) SRI_TRY(launch_stage_dmma<sri::kStagePosition>(h, p));
+    else SRI_TRY(launch_fused16<false>(h, p));
     return st.finish();
 }
 
@@ -700,7 +720,16 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
     SRI_TRY(st.in(fbar, (size_t)batch * 3 * N, &p.fbar));
     SRI_TRY(st.in(F_tip, (size_t)batch * 3, &p.F_tip));
     SRI_TRY(st.out(n, (size_t)batch * 3 * M, &p.n));
-    SRI_TRY(launch_fused16<false>(h, p));
+    if (h->R == 0 && !p.fbar) {
+        const long long total = (long long)batch * 3 * M;
+        sri::stress_noload_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, M, h->d_ops16 + sri::OpsLayout16::gT, p.F_tip, p.n);
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+    } else if (h->R == 0) {
+        SRI_TRY(launch_stage_dmma<sri::kStageStress>(h, p));
+    } else {
+        SRI_TRY(launch_fused16<false>(h, p));
+    }
     return st.finish();
 }
 
@@ -721,7 +750,8 @@ int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const dou
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     p.F_tip = p.M_tip;  // unused when nin is given; keeps the pointer valid
     SRI_TRY(st.out(m, (size_t)batch * 3 * M, &p.m));
-    SRI_TRY(launch_fused16<false>(h, p));
+    if (h->R == 0) SRI_TRY(launch_stage_dmma<sri::kStageCouple>(h, p));
+    else SRI_TRY(launch_fused16<false>(h, p));
     return st.finish();
 }
 

@@ -1,0 +1,145 @@
+// sri_stage_dmma.cuh -- the strain-independent stages as batched FP64 tensor-core contractions (N <= 16).
+//
+// Position (main.cpp:121-176), internal force and internal couple (rod_modeling.pdf eqs. 1.17-1.18) are all
+//      Out[i, (rod,c)] = sum_j T[i,j] * Rhs[j, (rod,c)],   T = Dn_NN^-1 or D_TT^-1 (cached, 15 x 15 padded to 16 x 16),
+// i.e. one small constant matrix applied to a very wide right-hand side: 2.7 kflop against ~0.8 KB per rod, so the
+// roofline is HBM.  Mapping onto DMMA (mma.sync.m8n8k4.f64), one warp per tile of 8 rods:
+//   * A fragments: T as 2 (m) x 4 (k) tiles of 8 x 4 -> 8 doubles per lane, loaded once per kernel;
+//   * B fragments: lane l owns rod l/4 of the tile and the four nodes 4*kt + l%4.  It loads exactly the inputs of
+//     those (rod, node) pairs (32-byte segments per rod, every byte of the tile read once, by one lane), evaluates the
+//     pointwise right-hand side (R(q)Gamma, -fbar - D_TI F, -(r' x n + lbar) - D_TI M) in registers, and the three
+//     components ARE its B fragments -- nothing is staged through shared memory;
+//   * C fragments: lane l holds output nodes 8*mt + l/4 of rods 2*(l%4), 2*(l%4)+1 -> 64-byte segments per rod on the
+//     way out.
+// 24 DMMA per 8 rods; the kernel keeps ~4 KB of loads in flight per warp and many warps per SM to cover HBM latency.
+#pragma once
+#include "sri_device.cuh"
+#include "sri_fused16.cuh"  // FusedParams, OpsLayout16
+
+namespace sri {
+
+enum StageKind { kStagePosition = 0, kStageStress = 1, kStageCouple = 2 };
+
+// Row-major 16 x 16 zero-padded copies of the two cached inverses, appended to the OpsLayout16 table.
+struct StageTables {
+    static constexpr int Srm = OpsLayout16::total;        // [16][16]  Dn_NN^-1
+    static constexpr int STrm = Srm + 256;                // [16][16]  D_TT^-1
+    static constexpr int total = STrm + 256;
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
+    const int lane = threadIdx.x & 31;
+    const int lr = lane >> 2, lk = lane & 3;  // tile-local rod (B/C row group) and k offset
+    const int M = p.M, N = p.N;
+    const double* T = p.ops + (STAGE == kStagePosition ? StageTables::Srm : StageTables::STrm);
+
+    // A fragments: a[mt][kt] = T[8*mt + lane/4][4*kt + lane%4]
+    double a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) a[mt][kt] = T[(8 * mt + lr) * 16 + 4 * kt + lk];
+    double dti[4], gvec[2];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) dti[kt] = p.ops[OpsLayout16::DTI + 4 * kt + lk];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) gvec[mt] = p.ops[OpsLayout16::g + 8 * mt + lr];
+
+    const long long tiles = (p.batch + 7) >> 3;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < tiles; tile += warps_total) {
+        const long long rod = tile * 8 + lr;
+        const bool live = rod < p.batch;
+
+        // ---- pointwise right-hand side of this lane's four (rod, node) pairs = B fragments -----------------
+        double bf[3][4];
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0;  // per-rod tip wrench (stress: F_tip, couple: M_tip)
+        if (STAGE == kStageStress && live) { const double* s = p.F_tip + rod * 3; w0 = s[0]; w1 = s[1]; w2 = s[2]; }
+        if (STAGE == kStageCouple && live) { const double* s = p.M_tip + rod * 3; w0 = s[0]; w1 = s[1]; w2 = s[2]; }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const int j = 4 * kt + lk;  // node (position) or reduced row (stress / couple)
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            if (live && j < M) {
+                if (STAGE == kStagePosition || STAGE == kStageCouple) {
+                    const int node = (STAGE == kStageCouple) ? j + 1 : j;
+                    quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+                    if (node < M) {
+                        const double* s = p.Qin + rod * 4 * M + node;
+                        q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M];
+                    } else if (p.q0) {
+                        const double* s = p.q0 + rod * 4;
+                        q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3];
+                    }
+                    double b0, b1, b2;
+                    if (p.Gamma) { const double* gm = p.Gamma + rod * 3 * N + node; q_rotate(q, gm[0], gm[N], gm[2 * N], b0, b1, b2); }
+                    else q_rotate_e1(q, b0, b1, b2);
+                    if (STAGE == kStagePosition) { r0 = b0; r1 = b1; r2 = b2; }
+                    else {
+                        const double* s = p.nin + rod * 3 * M + j;
+                        const double n0 = s[0], n1 = s[M], n2 = s[2 * M];
+                        double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+                        if (p.lbar) { const double* lb = p.lbar + rod * 3 * N + j + 1; l0 = lb[0]; l1 = lb[N]; l2 = lb[2 * N]; }
+                        r0 = -((b1 * n2 - b2 * n1) + l0) - dti[kt] * w0;
+                        r1 = -((b2 * n0 - b0 * n2) + l1) - dti[kt] * w1;
+                        r2 = -((b0 * n1 - b1 * n0) + l2) - dti[kt] * w2;
+                    }
+                } else {  // stress
+                    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+                    if (p.fbar) { const double* s = p.fbar + rod * 3 * N + j + 1; f0 = s[0]; f1 = s[N]; f2 = s[2 * N]; }
+                    r0 = -f0 - dti[kt] * w0; r1 = -f1 - dti[kt] * w1; r2 = -f2 - dti[kt] * w2;
+                }
+            }
+            bf[0][kt] = r0; bf[1][kt] = r1; bf[2][kt] = r2;
+        }
+
+        // ---- Out = T * Rhs on the FP64 tensor cores ---------------------------------------------------------
+        double acc[3][2][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                acc[c][mt][0] = 0.0; acc[c][mt][1] = 0.0;
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt) dmma_m8n8k4(acc[c][mt][0], acc[c][mt][1], a[mt][kt], bf[c][kt]);
+            }
+
+        // ---- epilogue: C fragment (node 8*mt + lane/4, rods 2*(lane%4) + {0,1}) -> [rod][c][node] ---------------
+        double* out = (STAGE == kStagePosition) ? p.r : (STAGE == kStageStress ? p.n : p.m);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const long long orod = tile * 8 + 2 * lk + w;
+            if (orod >= p.batch) continue;
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+            if (STAGE == kStagePosition && p.r0) { const double* s = p.r0 + orod * 3; e0 = s[0]; e1 = s[1]; e2 = s[2]; }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int i = 8 * mt + lr;
+                if (i >= M) continue;
+                double* d = out + orod * 3 * M + i;
+                d[0] = fma(gvec[mt], e0, acc[0][mt][w]);
+                d[M] = fma(gvec[mt], e1, acc[1][mt][w]);
+                d[2 * M] = fma(gvec[mt], e2, acc[2][mt][w]);
+            }
+        }
+    }
+}
+
+// n_i = gT_i F_tip when there is no distributed load: pure streaming, no contraction needed.
+__global__ void stress_noload_kernel(long long batch, int M, const double* __restrict__ gT, const double* __restrict__ F_tip,
+                                     double* __restrict__ n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * 3 * M) return;
+    const int i = (int)(idx % M);
+    const long long bc = idx / M;
+    n[idx] = gT[i] * F_tip[bc];
+}
+
+}  // namespace sri
