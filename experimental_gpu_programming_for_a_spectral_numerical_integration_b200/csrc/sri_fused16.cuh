@@ -141,6 +141,9 @@ __device__ __forceinline__ unsigned segment_max16(unsigned key) {
 #ifndef SRI_BCAST_SHFL
 #define SRI_BCAST_SHFL 0  // 0: pivot row through shared memory; 1: SHFL.IDX
 #endif
+#ifndef SRI_WINDOWS
+#define SRI_WINDOWS 4  // number of window-size classes (elimination loop bodies): 4, 3 or 2
+#endif
 #ifndef SRI_GROUP
 #define SRI_GROUP 3  // quaternion updates interleaved level by level
 #endif
@@ -158,9 +161,12 @@ __device__ __forceinline__ unsigned segment_max16(unsigned key) {
 //   equations:  sum_j Q_j (x) c_ij = b_i.   Row i takes  c_ij -= u_j (x) m_i  with u = pivot row and
 //   m_i = c_pk^-1 (x) c_ik; the pivot row takes m_p = 1 - c_pk^-1, which normalises it with the same update.
 // On entry key/cand describe slot 0 (key already segment-reduced); on exit they describe the new slot 0.
-template <int L>
-__device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, int row, double* pbuf, bool& used,
-                                               int& mycol, int& sing, unsigned& key, quat& cand) {
+template <int L, int NC>
+__device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, int live, int row, double* pbuf,
+                                               bool& used, int& mycol, int& sing, unsigned& key, quat& cand) {
+    // live = number of window slots that still hold columns (M - k); a body with window L and NC conditional slots
+    // serves live in (L-1-NC, L]: slots 1..L-1-NC are always live, the last NC slots only while slot < live
+    // (warp-uniform tests).
     const int prow = 15 - (int)(key & 15u);
     const bool is_pivot = (row == prow) && !used;
     if ((key >> 4) == 0u && sing == 0) sing = k + 1;
@@ -170,13 +176,14 @@ __device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, in
 #define SRI_PIVOT_RHS() shfl_quat(b, src)
     const quat pinv = shfl_quat(cand, src);
 #else
-    // the pivot lane publishes c_pk^-1 (slot 0), its window (slots 1..L-1) and its rhs (slot 15)
+    // the pivot lane publishes c_pk^-1 (slot 0), its live window slots and its rhs (slot 15)
     double* buf = pbuf + (k & 1) * (16 * 4);
     if (is_pivot) {
         st_quat(buf, cand);
-#pragma unroll
-        for (int j = 1; j < L; ++j) st_quat(buf + 4 * j, c[j]);
         st_quat(buf + 4 * 15, b);
+#pragma unroll
+        for (int j = 1; j < L; ++j)
+            if (j <= L - 1 - NC || j < live) st_quat(buf + 4 * j, c[j]);
     }
     __syncwarp();
 #define SRI_PIVOT_ROW(j) ld_quat(buf + 4 * (j))
@@ -185,51 +192,39 @@ __device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, in
 #endif
     quat mlt = q_mul_tree(pinv, c[0]);
     if (is_pivot) { mlt.w = 1.0 - pinv.w; mlt.x = -pinv.x; mlt.y = -pinv.y; mlt.z = -pinv.z; mycol = k; used = true; }
-    // Items 0..L-1 of this step: item t < L-1 is window slot t+1 (result goes to slot t), item L-1 is the rhs.
-    // A dependent DFMA waits ~36 cycles while the pipe takes a new one every 2, so items are processed in groups of
-    // SRI_GROUP with their four FMA levels interleaved (SRI_GROUP x 4 independent chains in flight per warp).
-    // The first group contains slot 1, the next pivot column: its candidate and the butterfly follow immediately
-    // and hide behind the remaining groups.
+    // slot 1 first: it becomes the next pivot column, and its candidate/key latency hides behind the bulk update
+    if (L > 1 && (1 <= L - 1 - NC || 1 < live)) {
+        const quat u = SRI_PIVOT_ROW(1);
+        quat t = c[L > 1 ? 1 : 0];
+        q_sub_mul(t, u, mlt);
+        c[0] = t;
+    } else {
+        c[0].w = 0.0; c[0].x = 0.0; c[0].y = 0.0; c[0].z = 0.0;
+    }
+    pivot_candidate(c[0], used, row, key, cand);
+    {
+        const quat u = SRI_PIVOT_RHS();
+        q_sub_mul(b, u, mlt);
+    }
     unsigned other = 0u;
-    int stage_done = 0;
 #pragma unroll
-    for (int t0 = 0; t0 < L; t0 += SRI_GROUP) {
-        quat u[SRI_GROUP], acc[SRI_GROUP];
-#pragma unroll
-        for (int g = 0; g < SRI_GROUP; ++g) {
-            const int t = t0 + g;
-            if (t < L - 1) { u[g] = SRI_PIVOT_ROW(t + 1 < 15 ? t + 1 : 14); acc[g] = c[t + 1 < 15 ? t + 1 : 14]; }
-            else if (t == L - 1) { u[g] = SRI_PIVOT_RHS(); acc[g] = b; }
+    for (int j = 2; j < L; ++j) {
+        const int stage = j - 2;  // butterfly stage interleaved with this slot
+        if (stage < 4) other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage);
+        if (j <= L - 1 - NC || j < live) {
+            const quat u = SRI_PIVOT_ROW(j);
+            quat t = c[j];
+            q_sub_mul(t, u, mlt);
+            c[j - 1] = t;
+        } else {
+            c[j - 1].w = 0.0; c[j - 1].x = 0.0; c[j - 1].y = 0.0; c[j - 1].z = 0.0;
         }
-#pragma unroll
-        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<0>(acc[g], u[g], mlt);
-#pragma unroll
-        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<1>(acc[g], u[g], mlt);
-#pragma unroll
-        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<2>(acc[g], u[g], mlt);
-#pragma unroll
-        for (int g = 0; g < SRI_GROUP; ++g) if (t0 + g < L) q_sub_mul_level<3>(acc[g], u[g], mlt);
-#pragma unroll
-        for (int g = 0; g < SRI_GROUP; ++g) {
-            const int t = t0 + g;
-            if (t < L - 1) c[t < 15 ? t : 14] = acc[g];
-            else if (t == L - 1) b = acc[g];
-        }
-        if (t0 == 0) {
-            if (L == 1) { c[0].w = 0.0; c[0].x = 0.0; c[0].y = 0.0; c[0].z = 0.0; }
-            pivot_candidate(c[0], used, row, key, cand);
-        } else if (stage_done < 4) {
-            // two butterfly stages per later group
-            other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage_done); key = key > other ? key : other; ++stage_done;
-            if (stage_done < 4) { other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage_done); key = key > other ? key : other; ++stage_done; }
-        }
+        if (stage < 4) key = key > other ? key : other;
     }
 #pragma unroll
-    for (int stage = 0; stage < 4; ++stage) {
-        if (stage >= stage_done) {
-            other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage);
-            key = key > other ? key : other;
-        }
+    for (int stage = (L - 2 > 0 ? L - 2 : 0); stage < 4; ++stage) {
+        other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage);
+        key = key > other ? key : other;
     }
     if (L > 1) { c[L - 1].w = 0.0; c[L - 1].x = 0.0; c[L - 1].y = 0.0; c[L - 1].z = 0.0; }
 #undef SRI_PIVOT_ROW
@@ -248,15 +243,29 @@ __device__ __forceinline__ void gauss_jordan16(quat (&c)[15], quat& b, int M, in
     pivot_candidate(c[0], used, row, key, cand);
     key = segment_max16(key);
     int k = 0;
-    const int e0 = M < 4 ? M : 4, e1 = M < 8 ? M : 8, e2 = M < 12 ? M : 12;
+    // the body is chosen by the live width M - k, so a short system (N < 16) starts directly with a small window
+#if SRI_WINDOWS == 4
 #pragma unroll 1
-    for (; k < e0; ++k) gj_step_rolled<15>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+    for (; M - k > 11; ++k) gj_step_rolled<15, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
 #pragma unroll 1
-    for (; k < e1; ++k) gj_step_rolled<11>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+    for (; M - k > 7; ++k) gj_step_rolled<11, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
 #pragma unroll 1
-    for (; k < e2; ++k) gj_step_rolled<7>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+    for (; M - k > 3; ++k) gj_step_rolled<7, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
 #pragma unroll 1
-    for (; k < M; ++k) gj_step_rolled<3>(c, b, k, row, pbuf, used, mycol, sing, key, cand);
+    for (; M - k > 0; ++k) gj_step_rolled<3, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
+#elif SRI_WINDOWS == 3
+#pragma unroll 1
+    for (; M - k > 10; ++k) gj_step_rolled<15, 4>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
+#pragma unroll 1
+    for (; M - k > 5; ++k) gj_step_rolled<10, 4>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
+#pragma unroll 1
+    for (; M - k > 0; ++k) gj_step_rolled<5, 5>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
+#else
+#pragma unroll 1
+    for (; M - k > 7; ++k) gj_step_rolled<15, 7>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
+#pragma unroll 1
+    for (; M - k > 0; ++k) gj_step_rolled<7, 7>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
+#endif
 }
 
 // out_c = sum_j T[j*16+row] * v[j][c], c = 0..2, with three interleaved partial sums per component so that the
