@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -722,7 +723,7 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
     SRI_TRY(st.out(n, (size_t)batch * 3 * M, &p.n));
     if (h->R == 0 && !p.fbar) {
         const long long total = (long long)batch * 3 * M;
-        sri::stress_noload_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, M, h->d_ops16 + sri::OpsLayout16::gT, p.F_tip, p.n);
+        sri::stress_noload_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16), 256, 0, h->stream>>>(batch, M, h->d_ops16 + sri::OpsLayout16::gT, p.F_tip, p.n);
         g_launches.fetch_add(1);
         SRI_CUDA(cudaGetLastError());
     } else if (h->R == 0) {

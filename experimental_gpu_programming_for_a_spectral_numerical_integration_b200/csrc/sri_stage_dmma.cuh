@@ -135,11 +135,12 @@ __global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
 // n_i = gT_i F_tip when there is no distributed load: pure streaming, no contraction needed.
 __global__ void stress_noload_kernel(long long batch, int M, const double* __restrict__ gT, const double* __restrict__ F_tip,
                                      double* __restrict__ n) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= batch * 3 * M) return;
-    const int i = (int)(idx % M);
-    const long long bc = idx / M;
-    n[idx] = gT[i] * F_tip[bc];
+    const long long total = batch * 3 * M;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int i = (int)(idx % M);
+        n[idx] = gT[i] * __ldg(F_tip + idx / M);
+    }
 }
 
 }  // namespace sri

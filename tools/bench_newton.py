@@ -33,7 +33,7 @@ h.generate_rods(0x5EED, lo, B, None, F, None, None)
 F[:, 2] = -(F[:, 2] + 1.0); F[:, :2] = 0.0
 Mt = torch.zeros((B, 3), dtype=torch.float64, device=dev)
 solver = StaticShapeSolver(h, (1.0, 1.0, 0.77), ne=args.ne)
-solver.solve(F[:1024], Mt[:1024]) if world == 1 else None   # warm-up (single rank only: collectives must match)
+solver.solve(F[:1024].clone(), Mt[:1024].clone(), max_iter=2)   # warm-up; every rank takes part, so the collectives match
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 l0 = kernel_launch_count()
