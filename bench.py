@@ -70,9 +70,17 @@ def _time_oracle(o, rods: int, first_rod: int, explicit_inverse: bool, nthreads:
     return dt
 
 
+def _host_cores() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(target_seconds: float):
     o, how = _native_oracle()
-    cores = o.max_threads()
+    cores = _host_cores()
     probe = 1024 * cores
     _time_oracle(o, probe, 0, True, cores)  # warm up threads and caches
     dt = _time_oracle(o, probe, 0, True, cores)
@@ -96,7 +104,7 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     o, how = _native_oracle()
-    cores = o.max_threads()
+    cores = _host_cores()
     probe = 1024 * cores
     _time_oracle(o, probe, 0, True, cores)
     rate = probe / _time_oracle(o, probe, 0, True, cores)
