@@ -13,6 +13,7 @@
 #include "sri_fused16.cuh"
 #include "sri_generic.cuh"
 #include "sri_stage_dmma.cuh"
+#include "sri_tiled.cuh"
 #include "sri_host_math.hpp"
 
 namespace {
@@ -324,11 +325,12 @@ constexpr size_t kFusedSmem = (sri::OpsLayout16::total + (kFusedThreads / 32) * 
 template <bool SOLVE>
 int launch_generic(sri_context* h, const sri::FusedParams& p, cudaStream_t stream) {
     const long long cap = (long long)h->sm_count * h->generic_blocks_per_sm;
-    const int grid = (int)(p.batch < cap ? p.batch : cap);
+    const long long groups = (h->R == 32) ? (p.batch + 1) / 2 : p.batch;  // rods per CTA iteration: 2 (N <= 32) or 1
+    const int grid = (int)(groups < cap ? groups : cap);
     if (h->R == 32)
-        sri::generic_kernel<32, SOLVE><<<grid, 128, h->generic_smem, stream>>>(p);
+        sri::tiled_kernel<16, 4, SOLVE><<<grid, 128, h->generic_smem, stream>>>(p);
     else
-        sri::generic_kernel<64, SOLVE><<<grid, 256, h->generic_smem, stream>>>(p);
+        sri::tiled_kernel<32, 8, SOLVE><<<grid, 256, h->generic_smem, stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return SRI_OK;
@@ -528,7 +530,7 @@ int sri_create(int N, int device, sri_handle* out) {
         SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * sri::StageTables::total));
         SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * sri::StageTables::total, cudaMemcpyHostToDevice));
     } else {
-        h->R = (M <= 32) ? 32 : 64;
+        h->R = (M <= 31) ? 32 : 64;  // row capacity / table stride of the tiled kernel
         const sri::OpsLayoutGeneric L{h->R};
         std::vector<double> t(L.total(), 0.0);
         for (int j = 0; j < M; ++j)
@@ -543,15 +545,16 @@ int sri_create(int N, int device, sri_handle* out) {
         }
         SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * L.total()));
         SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * L.total(), cudaMemcpyHostToDevice));
-        h->generic_smem = sri::generic_smem_doubles(M, h->R) * sizeof(double);
         if (h->R == 32) {
-            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
-            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
-            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::generic_kernel<32, true>, 128, h->generic_smem));
+            h->generic_smem = sri::TiledSmem<16, 4>::total() * sizeof(double);
+            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::tiled_kernel<16, 4, true>, 128, h->generic_smem));
         } else {
-            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
-            SRI_CUDA(cudaFuncSetAttribute(sri::generic_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
-            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::generic_kernel<64, true>, 256, h->generic_smem));
+            h->generic_smem = sri::TiledSmem<32, 8>::total() * sizeof(double);
+            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<32, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<32, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::tiled_kernel<32, 8, true>, 256, h->generic_smem));
         }
         if (h->generic_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: generic kernel does not fit on this device"); }
     }
