@@ -108,7 +108,8 @@ def run_reference(args, rank: int):
     probe = 1024 * cores
     _time_oracle(o, probe, 0, True, cores)
     rate = probe / _time_oracle(o, probe, 0, True, cores)
-    per_step = int(min(max(rate * 6.0, probe), 1_000_000))  # ~6 s of host work per step
+    per_step_seconds = min(6.0, 90.0 / max(args.steps, 1))  # keeps the whole run within a couple of minutes
+    per_step = int(min(max(rate * per_step_seconds, probe), 1_000_000))
     for _ in range(args.warmup):
         _time_oracle(o, min(per_step, 4 * probe), 0, True, cores)
     total = 0.0
@@ -284,6 +285,23 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                "path": "sri_integrate_all() with pinned host buffers; per step: H2D of K,F_tip,M_tip,fbar, fused kernel, D2H of Q,r,n,m"}
         barrier()
 
+    # ---- BASELINE configs[1] (10^4 rods on one GPU) timed beside the headline workload, device-resident ----------
+    cfg2 = None
+    if world == 1:
+        Bs = 10_000
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        small = lambda: h.integrate_all(K[:Bs], F[:Bs], Mt[:Bs], fbar=fb[:Bs], Q=Q[:Bs], r=r[:Bs], n=n[:Bs], m=m[:Bs])
+        for _ in range(5):
+            small()
+        torch.cuda.synchronize(dev)
+        e2.record(stream)
+        for _ in range(50):
+            small()
+        e3.record(stream)
+        torch.cuda.synchronize(dev)
+        cfg2 = {"workload": "cfg2: 10^4 rods, N=16, 1 GPU (a single 2.8-wave launch; L2-resident after the first pass)",
+                "rods_per_s": Bs / (e2.elapsed_time(e3) / 50 * 1e-3), "us_per_launch": e2.elapsed_time(e3) / 50 * 1e3}
+
     if rank != 0:
         return
 
@@ -326,6 +344,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                    "l2": f"inputs+outputs {BYTES_PER_ROD * B / 1e6:.0f} MB per step > 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
+    if cfg2 is not None:
+        line["other_configs"] = {"cfg2": cfg2}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     print(json.dumps(line), flush=True)

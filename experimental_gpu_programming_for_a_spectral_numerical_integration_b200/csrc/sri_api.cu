@@ -346,10 +346,14 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p, cudaStream_t strea
     const int per_sm = SOLVE ? h->fused_blocks_per_sm : h->stage_blocks_per_sm;
     const long long cap = (long long)h->sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    if (h->M == 15)
-        sri::fused16_kernel<15, SOLVE><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
-    else
-        sri::fused16_kernel<0, SOLVE><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
+    if constexpr (!SOLVE) {
+        return fail(SRI_ERR_INVALID_ARGUMENT, "internal: the N <= 16 stage entry points use the DMMA stage kernels");
+    } else {
+        if (h->M == 15)
+            sri::fused16_kernel<15, true><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
+        else
+            sri::fused16_kernel<0, true><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
+    }
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return SRI_OK;
@@ -575,10 +579,10 @@ int sri_create(int N, int device, sri_handle* out) {
         h->fused_blocks_per_sm = h->stage_blocks_per_sm = h->generic_blocks_per_sm;
     } else if (M == 15) {
         SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_blocks_per_sm, sri::fused16_kernel<15, true>, kFusedThreads, kFusedSmem));
-        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->stage_blocks_per_sm, sri::fused16_kernel<15, false>, kFusedThreads, kFusedSmem));
+        h->stage_blocks_per_sm = h->fused_blocks_per_sm;
     } else {
         SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_blocks_per_sm, sri::fused16_kernel<0, true>, kFusedThreads, kFusedSmem));
-        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->stage_blocks_per_sm, sri::fused16_kernel<0, false>, kFusedThreads, kFusedSmem));
+        h->stage_blocks_per_sm = h->fused_blocks_per_sm;
     }
     if (h->fused_blocks_per_sm < 1 || h->stage_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: kernel does not fit on this device"); }
     *out = h;
