@@ -370,21 +370,24 @@ __global__ void __launch_bounds__(128, SOLVE ? SRI_MINBLOCKS : 4) fused16_kernel
         quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
         if (SOLVE) {
             // ---- stage 1: assemble c_ij = delta_ij - 1/2 S_ij (0,K_j) and eliminate ---------------------
-            quat c[15], b;
-#pragma unroll
-            for (int j = 0; j < 15; ++j) {
-                const double s = tab[OpsLayout16::St + j * MP16 + row];  // -1/2 S_ij
-                c[j].w = (j == row) ? 1.0 : 0.0;
-                c[j].x = s * kb[j]; c[j].y = s * kb[16 + j]; c[j].z = s * kb[32 + j];
-            }
+            int sing;
             {
-                const double gi = tab[OpsLayout16::g + row];
-                b.w = gi * q0.w; b.x = gi * q0.x; b.y = gi * q0.y; b.z = gi * q0.z;
+                quat c[15], b;
+#pragma unroll
+                for (int j = 0; j < 15; ++j) {
+                    const double s = tab[OpsLayout16::St + j * MP16 + row];  // -1/2 S_ij
+                    c[j].w = (j == row) ? 1.0 : 0.0;
+                    c[j].x = s * kb[j]; c[j].y = s * kb[16 + j]; c[j].z = s * kb[32 + j];
+                }
+                {
+                    const double gi = tab[OpsLayout16::g + row];
+                    b.w = gi * q0.w; b.x = gi * q0.x; b.y = gi * q0.y; b.z = gi * q0.z;
+                }
+                int mycol;
+                gauss_jordan16(c, b, M, row, scr + RodScratch::pbuf, mycol, sing);
+                __syncwarp();
+                if (row < M) st_quat(qnode + 4 * mycol, b);
             }
-            int mycol, sing;
-            gauss_jordan16(c, b, M, row, scr + RodScratch::pbuf, mycol, sing);
-            __syncwarp();
-            if (row < M) st_quat(qnode + 4 * mycol, b);
             if (row == M) st_quat(qnode + 4 * M, q0);
             if (p.info && live && row == 0) p.info[rod] = sing;
             cp_async_wait<0>();
