@@ -216,9 +216,7 @@ __device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, in
             quat t = c[j];
             q_sub_mul(t, u, mlt);
             c[j - 1] = t;
-        } else {
-            c[j - 1].w = 0.0; c[j - 1].x = 0.0; c[j - 1].y = 0.0; c[j - 1].z = 0.0;
-        }
+        }  // a slot >= live is dead: it is never published, loaded or updated again, so it needs no zero fill
         if (stage < 4) key = key > other ? key : other;
     }
 #pragma unroll
@@ -226,7 +224,6 @@ __device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, in
         other = __shfl_xor_sync(0xffffffffu, key, 8 >> stage);
         key = key > other ? key : other;
     }
-    if (L > 1) { c[L - 1].w = 0.0; c[L - 1].x = 0.0; c[L - 1].y = 0.0; c[L - 1].z = 0.0; }
 #undef SRI_PIVOT_ROW
 #undef SRI_PIVOT_RHS
 }
