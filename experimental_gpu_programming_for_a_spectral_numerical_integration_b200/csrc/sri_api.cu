@@ -319,7 +319,7 @@ __global__ void fp64_peak_kernel(double* out, int iters, double s) {
 
 // ---- launch helpers --------------------------------------------------------------------------------------------
 
-constexpr int kFusedThreads = 128;
+constexpr int kFusedThreads = SRI_THREADS;
 constexpr size_t kFusedSmem = (sri::OpsLayout16::total + (kFusedThreads / 32) * sri::kWarpScratch16) * sizeof(double);
 
 template <bool SOLVE>

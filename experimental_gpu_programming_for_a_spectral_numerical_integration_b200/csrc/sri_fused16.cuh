@@ -27,6 +27,9 @@ constexpr int MP16 = 16;  // padded rows per rod in this kernel
 #ifndef SRI_MINBLOCKS
 #define SRI_MINBLOCKS 3
 #endif
+#ifndef SRI_THREADS
+#define SRI_THREADS 128  // threads per CTA of the fused kernel
+#endif
 
 // Packed operator tables (doubles), stride MP16, zero padded.  Built on the host by sri_api.cu.
 struct OpsLayout16 {
@@ -291,7 +294,7 @@ __device__ __forceinline__ void contract16(const double* T, const double* v, int
 // SOLVE = true: all stages starting from the strain samples K.  SOLVE = false: the cached-operator stages only
 // (position / stress / couple), reading Q (and optionally n) produced by an earlier call.
 template <int MS, bool SOLVE>
-__global__ void __launch_bounds__(128, SOLVE ? SRI_MINBLOCKS : 4) fused16_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(SRI_THREADS, SOLVE ? SRI_MINBLOCKS : 4) fused16_kernel(const FusedParams p) {
     extern __shared__ __align__(16) double smem[];
     double* tab = smem;  // OpsLayout16::total doubles
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
