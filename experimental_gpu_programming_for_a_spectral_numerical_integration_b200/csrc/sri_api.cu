@@ -518,7 +518,9 @@ int sri_create(int N, int device, sri_handle* out) {
             for (int j = 0; j < M; ++j) {
                 t[sri::StageTables::Srm + i * 16 + j] = h->ops.S[j * M + i];
                 t[sri::StageTables::STrm + i * 16 + j] = h->ops.ST[j * M + i];
+                t[sri::StageTables::STsh + i * 16 + j + 1] = h->ops.ST[j * M + i];
             }
+        for (int j = 0; j < M; ++j) t[sri::StageTables::DTIsh + j + 1] = h->ops.D_TI[j];
         for (int j = 0; j < M; ++j)
             for (int i = 0; i < M; ++i) {
                 t[L::St + j * sri::MP16 + i] = -0.5 * h->ops.S[j * M + i];

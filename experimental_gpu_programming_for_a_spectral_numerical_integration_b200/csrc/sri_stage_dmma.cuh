@@ -24,7 +24,10 @@ enum StageKind { kStagePosition = 0, kStageStress = 1, kStageCouple = 2 };
 struct StageTables {
     static constexpr int Srm = OpsLayout16::total;        // [16][16]  Dn_NN^-1
     static constexpr int STrm = Srm + 256;                // [16][16]  D_TT^-1
-    static constexpr int total = STrm + 256;
+    static constexpr int STsh = STrm + 256;               // [16][16]  D_TT^-1 with columns shifted by one: STsh[i][node] =
+                                                          //           D_TT^-1[i][node-1], column 0 zero (k index = node)
+    static constexpr int DTIsh = STsh + 256;              // [16]      D_TI shifted the same way (DTIsh[node] = D_TI[node-1])
+    static constexpr int total = DTIsh + 16;
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -38,7 +41,10 @@ __global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
     const int lane = threadIdx.x & 31;
     const int lr = lane >> 2, lk = lane & 3;  // tile-local rod (B/C row group) and k offset
     const int M = p.M, N = p.N;
-    const double* T = p.ops + (STAGE == kStagePosition ? StageTables::Srm : StageTables::STrm);
+    // Stress and couple contract over the reduced rows j' = node - 1.  Using the NODE as the k index (shifted table,
+    // zero column for node 0) makes this lane's four k values the nodes 4*kt + l%4, so its loads of the nodal inputs
+    // (fbar, lbar, Q, Gamma) are 32-byte aligned segments instead of segments straddling two sectors.
+    const double* T = p.ops + (STAGE == kStagePosition ? StageTables::Srm : StageTables::STsh);
 
     // A fragments: a[mt][kt] = T[8*mt + lane/4][4*kt + lane%4]
     double a[2][4];
@@ -48,7 +54,7 @@ __global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
         for (int kt = 0; kt < 4; ++kt) a[mt][kt] = T[(8 * mt + lr) * 16 + 4 * kt + lk];
     double dti[4], gvec[2];
 #pragma unroll
-    for (int kt = 0; kt < 4; ++kt) dti[kt] = p.ops[OpsLayout16::DTI + 4 * kt + lk];
+    for (int kt = 0; kt < 4; ++kt) dti[kt] = p.ops[StageTables::DTIsh + 4 * kt + lk];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) gvec[mt] = p.ops[OpsLayout16::g + 8 * mt + lr];
 
@@ -65,11 +71,11 @@ __global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
         if (STAGE == kStageCouple && live) { const double* s = p.M_tip + rod * 3; w0 = s[0]; w1 = s[1]; w2 = s[2]; }
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
-            const int j = 4 * kt + lk;  // node (position) or reduced row (stress / couple)
+            const int node = 4 * kt + lk;  // k index of this lane = node; stress / couple use reduced row node - 1
             double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-            if (live && j < M) {
+            const bool valid = (STAGE == kStagePosition) ? (node < M) : (node >= 1 && node <= M);
+            if (live && valid) {
                 if (STAGE == kStagePosition || STAGE == kStageCouple) {
-                    const int node = (STAGE == kStageCouple) ? j + 1 : j;
                     quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
                     if (node < M) {
                         const double* s = p.Qin + rod * 4 * M + node;
@@ -83,17 +89,17 @@ __global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
                     else q_rotate_e1(q, b0, b1, b2);
                     if (STAGE == kStagePosition) { r0 = b0; r1 = b1; r2 = b2; }
                     else {
-                        const double* s = p.nin + rod * 3 * M + j;
+                        const double* s = p.nin + rod * 3 * M + node - 1;
                         const double n0 = s[0], n1 = s[M], n2 = s[2 * M];
                         double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-                        if (p.lbar) { const double* lb = p.lbar + rod * 3 * N + j + 1; l0 = lb[0]; l1 = lb[N]; l2 = lb[2 * N]; }
+                        if (p.lbar) { const double* lb = p.lbar + rod * 3 * N + node; l0 = lb[0]; l1 = lb[N]; l2 = lb[2 * N]; }
                         r0 = -((b1 * n2 - b2 * n1) + l0) - dti[kt] * w0;
                         r1 = -((b2 * n0 - b0 * n2) + l1) - dti[kt] * w1;
                         r2 = -((b0 * n1 - b1 * n0) + l2) - dti[kt] * w2;
                     }
                 } else {  // stress
                     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-                    if (p.fbar) { const double* s = p.fbar + rod * 3 * N + j + 1; f0 = s[0]; f1 = s[N]; f2 = s[2 * N]; }
+                    if (p.fbar) { const double* s = p.fbar + rod * 3 * N + node; f0 = s[0]; f1 = s[N]; f2 = s[2 * N]; }
                     r0 = -f0 - dti[kt] * w0; r1 = -f1 - dti[kt] * w1; r2 = -f2 - dti[kt] * w2;
                 }
             }
