@@ -33,6 +33,14 @@ FLOPS_PER_ROD_DENSE = 155_700
 BYTES_PER_ROD = 1_992 + 3 * N_NODES * 8  # compulsory HBM traffic incl. the nodal fbar this workload supplies
 
 
+def _config(rods: int, world: int) -> dict:
+    """The workload description shared by both arms."""
+    return {"workload": f"cfg3: {rods} rods per GPU, N=16, constant+linear strain (Philox seed 0x5EED, counter = rod "
+                        "index), random tip wrench, constant distributed load, all 4 stages fused",
+            "N": N_NODES, "rods_per_gpu": rods, "parallelism": f"rod-index sharding x{world}, no collective",
+            "l2": f"inputs+outputs {BYTES_PER_ROD * rods / 1e6:.0f} MB per step > 126 MB L2"}
+
+
 def _parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -122,8 +130,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rods/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg3: {args.rods} rods per GPU, N=16, constant+linear strain, 4 stages",
-                   "N": N_NODES, "rods_per_step_sampled": per_step},
+        "config": dict(_config(args.rods, args.gpus), rods_per_step_sampled=per_step),
         "cpu_baseline": {"value": value, "unit": "rods/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -338,10 +345,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": value, "unit": "rods/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg3: {B} rods per GPU, N=16, constant+linear strain (Philox seed 0x5EED, counter = rod "
-                               "index), random tip wrench, constant distributed load, all 4 stages fused",
-                   "N": N, "rods_per_gpu": B, "parallelism": f"rod-index sharding x{world}, no collective",
-                   "l2": f"inputs+outputs {BYTES_PER_ROD * B / 1e6:.0f} MB per step > 126 MB L2"},
+        "config": _config(B, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if cfg2 is not None:
