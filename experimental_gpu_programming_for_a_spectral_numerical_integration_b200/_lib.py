@@ -64,6 +64,7 @@ SYMBOLS = {
     "sri_generate_rods": (c_int, [c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_last_error_string": (c_char_p, []),
     "sri_kernel_launch_count": (c_int64, []),
+    "sri_get_handback_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "sri_measure_fp64_peak": (c_int, [c_void_p, POINTER(c_double)]),
 }
 

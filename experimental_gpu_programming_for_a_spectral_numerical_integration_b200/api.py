@@ -271,6 +271,12 @@ class SpectralRodIntegrator:
             "sri_generate_rods",
         )
 
+    def handback_count(self) -> int:
+        """Rods of the last device-buffer call that the DMMA elimination handed back to the row-pivoting kernel."""
+        v = ctypes.c_int64()
+        _lib.check(self._lib.sri_get_handback_count(self._h, ctypes.byref(v)), "sri_get_handback_count")
+        return int(v.value)
+
     def measure_fp64_peak(self) -> float:
         v = ctypes.c_double()
         _lib.check(self._lib.sri_measure_fp64_peak(self._h, ctypes.byref(v)), "sri_measure_fp64_peak")

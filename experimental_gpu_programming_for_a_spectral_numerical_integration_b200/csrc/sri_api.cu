@@ -6,11 +6,13 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "sri_fused16.cuh"
+#include "sri_fused16_dmma.cuh"
 #include "sri_generic.cuh"
 #include "sri_stage_dmma.cuh"
 #include "sri_tiled.cuh"
@@ -50,6 +52,12 @@ struct sri_context {
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
     int fused_blocks_per_sm = 0;
     int stage_blocks_per_sm = 0;
+    int dmma_blocks_per_sm = 0;
+    double dmma_growth = sri::kDmmaGrowthDefault;
+    bool use_dmma = false;       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
+    // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
+    int* d_list[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t list_cap[4] = {0, 0, 0, 0};
     // host-buffer pipeline: chunks of rods flow H2D -> kernel -> D2H on rotating streams with persistent staging
     static constexpr int kPipeSlots = 3;
     static constexpr int kPipeArrays = 13;
@@ -336,9 +344,24 @@ int launch_generic(sri_context* h, const sri::FusedParams& p, cudaStream_t strea
     return SRI_OK;
 }
 
+int list_reserve(sri_context* h, int slot, long long batch) {
+    const size_t need = (size_t)batch + 4;
+    if (h->list_cap[slot] < need) {
+        if (h->d_list[slot]) SRI_CUDA(cudaFree(h->d_list[slot]));
+        h->d_list[slot] = nullptr;
+        h->list_cap[slot] = 0;
+        SRI_CUDA(cudaMalloc(&h->d_list[slot], need * sizeof(int)));
+        h->list_cap[slot] = need;
+    }
+    return SRI_OK;
+}
+
+// list_slot: which hand-back list to use (pipeline slot, or 3 for the handle stream)
 template <bool SOLVE>
-int launch_fused16(sri_context* h, const sri::FusedParams& p, cudaStream_t stream = nullptr, bool use_handle_stream = true) {
-    if (p.batch <= 0) return SRI_OK;
+int launch_fused16(sri_context* h, const sri::FusedParams& p_in, cudaStream_t stream = nullptr, bool use_handle_stream = true,
+                   int list_slot = 3) {
+    if (p_in.batch <= 0) return SRI_OK;
+    sri::FusedParams p = p_in;
     if (use_handle_stream) stream = h->stream;
     if (h->R != 0) return launch_generic<SOLVE>(h, p, stream);
     const long long pairs = (p.batch + 1) / 2;
@@ -349,6 +372,25 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p, cudaStream_t strea
     if constexpr (!SOLVE) {
         return fail(SRI_ERR_INVALID_ARGUMENT, "internal: the N <= 16 stage entry points use the DMMA stage kernels");
     } else {
+        if (h->use_dmma) {
+            if (p.batch > 0x7fffffffLL) return fail(SRI_ERR_INVALID_ARGUMENT, "batch too large for one call (2^31 rods)");
+            SRI_TRY(list_reserve(h, list_slot, p.batch));
+            p.growth2 = h->dmma_growth * h->dmma_growth;
+            p.rod_count = h->d_list[list_slot];
+            p.rod_list = h->d_list[list_slot] + 4;
+            SRI_CUDA(cudaMemsetAsync(p.rod_count, 0, sizeof(int), stream));
+            constexpr int wpc = sri::kDmmaThreads / 32;
+            const long long dwant = (p.batch + wpc - 1) / wpc;
+            const long long dcap = (long long)h->sm_count * h->dmma_blocks_per_sm;
+            const int dgrid = (int)(dwant < dcap ? dwant : dcap);
+            if (h->M == 15)
+                sri::fused16_dmma_kernel<15><<<dgrid, sri::kDmmaThreads, sri::kDmmaSmem, stream>>>(p);
+            else
+                sri::fused16_dmma_kernel<0><<<dgrid, sri::kDmmaThreads, sri::kDmmaSmem, stream>>>(p);
+            g_launches.fetch_add(1);
+            SRI_CUDA(cudaGetLastError());
+            // second pass (row pivoting) over the rods handed back; CTAs without work exit at once
+        }
         if (h->M == 15)
             sri::fused16_kernel<15, true><<<grid, kFusedThreads, kFusedSmem, stream>>>(p);
         else
@@ -420,7 +462,7 @@ int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
         p.F_tip = static_cast<const double*>(din[6]); p.M_tip = static_cast<const double*>(din[7]);
         p.Q = static_cast<double*>(dout[0]); p.r = static_cast<double*>(dout[1]); p.n = static_cast<double*>(dout[2]);
         p.m = static_cast<double*>(dout[3]); p.info = static_cast<int*>(dout[4]);
-        SRI_TRY(launch_fused16<true>(h, p, st, false));
+        SRI_TRY(launch_fused16<true>(h, p, st, false, slot));
         for (int a = 0; a < 5; ++a) {
             if (!outs[a].dst) continue;
             SRI_CUDA(cudaMemcpyAsync(static_cast<char*>(outs[a].dst) + (size_t)first * outs[a].per_rod, dout[a],
@@ -533,8 +575,13 @@ int sri_create(int N, int device, sri_handle* out) {
             t[L::DTI + i] = h->ops.D_TI[i];
             t[L::DnIN + i] = h->ops.Dn_IN[i];
         }
-        SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * sri::StageTables::total));
-        SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * sri::StageTables::total, cudaMemcpyHostToDevice));
+        t.resize(sri::DmmaTables::total, 0.0);
+        for (int i = 0; i < M; ++i) {
+            for (int j = 0; j < M; ++j) t[sri::DmmaTables::Stx + i * 16 + j] = -0.5 * h->ops.S[j * M + i];
+            t[sri::DmmaTables::Stx + i * 16 + 15] = h->ops.g[i];
+        }
+        SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * sri::DmmaTables::total));
+        SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * sri::DmmaTables::total, cudaMemcpyHostToDevice));
     } else {
         h->R = (M <= 31) ? 32 : 64;  // row capacity / table stride of the tiled kernel
         const sri::OpsLayoutGeneric L{h->R};
@@ -587,6 +634,16 @@ int sri_create(int N, int device, sri_handle* out) {
         h->stage_blocks_per_sm = h->fused_blocks_per_sm;
     }
     if (h->fused_blocks_per_sm < 1 || h->stage_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: kernel does not fit on this device"); }
+    if (N <= 16) {
+        if (M == 15) SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::fused16_dmma_kernel<15>, sri::kDmmaThreads, sri::kDmmaSmem));
+        else SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::fused16_dmma_kernel<0>, sri::kDmmaThreads, sri::kDmmaSmem));
+        if (h->dmma_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
+        // Both are sm_100a kernels of this library; SRI_FUSED16_IMPL=scalar selects the row-pivoting scalar kernel for
+        // every rod (A/B measurements), the default is the DMMA elimination with the scalar kernel as its second pass.
+        const char* impl = std::getenv("SRI_FUSED16_IMPL");
+        h->use_dmma = !(impl && std::strcmp(impl, "scalar") == 0);
+        if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
+    }
     *out = h;
     return SRI_OK;
 }
@@ -598,6 +655,8 @@ int sri_destroy(sri_handle h) {
     if (h->d_tnodes) cudaFree(h->d_tnodes);
     if (h->d_reduce) cudaFree(h->d_reduce);
     if (h->d_ccw) cudaFree(h->d_ccw);
+    for (int sl = 0; sl < 4; ++sl)
+        if (h->d_list[sl]) cudaFree(h->d_list[sl]);
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) {
         for (int a = 0; a < sri_context::kPipeArrays; ++a)
             if (h->pipe_buf[sl][a]) cudaFree(h->pipe_buf[sl][a]);
@@ -832,6 +891,18 @@ int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t ba
     generate_rods_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(seed, first_rod, batch, h->N, h->d_tnodes, K, F_tip, M_tip, fbar);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+int sri_get_handback_count(sri_handle h, int64_t* count) {
+    SRI_TRY(check_handle(h));
+    if (!count) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_handback_count: null argument");
+    *count = 0;
+    if (!h->use_dmma || !h->d_list[3]) return SRI_OK;
+    int c = 0;
+    SRI_CUDA(cudaMemcpyAsync(&c, h->d_list[3], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SRI_CUDA(cudaStreamSynchronize(h->stream));
+    *count = c;
     return SRI_OK;
 }
 

@@ -62,6 +62,11 @@ struct FusedParams {
     double* n;
     double* m;
     int* info;
+    // Rods that need row pivoting: written by the DMMA kernel (sri_fused16_dmma.cuh), then read by the scalar kernel,
+    // which in that mode integrates rods rod_list[0 .. *rod_count) instead of 0 .. batch.
+    int* rod_list;
+    int* rod_count;
+    double growth2;  // DMMA kernel: square of the accepted sub-diagonal growth max_{i>k} |c_ik| / |c_kk|
 };
 
 // Per-rod shared scratch (doubles).
@@ -305,19 +310,24 @@ __global__ void __launch_bounds__(SRI_THREADS, SOLVE ? SRI_MINBLOCKS : 4) fused1
     double* vec2 = scr + RodScratch::vec2;
     double* misc = scr + RodScratch::misc;
 
+    const bool listed = SOLVE && p.rod_list != nullptr;  // second pass over the rods the DMMA kernel handed back
+    const long long batch = listed ? (long long)*p.rod_count : p.batch;
+    const long long pairs = (batch + 1) >> 1;
+    if ((long long)blockIdx.x * (blockDim.x >> 5) >= pairs) return;  // whole CTA idle (the usual case of a second pass)
     for (int i = threadIdx.x; i < OpsLayout16::total; i += blockDim.x) tab[i] = p.ops[i];
     __syncthreads();
 
     const int M = MS ? MS : p.M;
     const int N = M + 1;
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long pairs = (p.batch + 1) >> 1;
     const long long pair0 = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
 
-    // strain samples (and q0) of rod `rod_` -> kbuf[slot]; lanes outside the rod / batch write zeros (q0: identity)
-    auto prefetch_K = [&](long long rod_, int slot) {
+    // strain samples (and q0) of the rod at position `idx_` -> kbuf[slot]; lanes outside the rod / batch write zeros
+    // (q0: identity)
+    auto prefetch_K = [&](long long idx_, int slot) {
         double* kb = scr + RodScratch::kbuf + slot * 64;
-        const bool ok = rod_ < p.batch;
+        const bool ok = idx_ < batch;
+        const long long rod_ = (ok && listed) ? (long long)p.rod_list[idx_] : idx_;
         if (SOLVE) {
             if (ok && row < N) {
                 const double* s = p.K + rod_ * 3 * N + row;
@@ -337,8 +347,9 @@ __global__ void __launch_bounds__(SRI_THREADS, SOLVE ? SRI_MINBLOCKS : 4) fused1
 
     int it = 0;
     for (long long pair = pair0; pair < pairs; pair += warps_total, ++it) {
-        const long long rod = 2 * pair + sub;
-        const bool live = rod < p.batch;
+        const long long idx = 2 * pair + sub;
+        const bool live = idx < batch;
+        const long long rod = (live && listed) ? (long long)p.rod_list[idx] : idx;
         const int cur = it & 1;
 
         // ---- prefetch: this pair's late inputs and the next pair's strain samples -----------------------

@@ -1,0 +1,362 @@
+// sri_fused16_dmma.cuh -- fused four-stage kernel for N <= 16 with the quaternion elimination on the FP64 tensor
+// cores (DMMA m8n8k4).  ONE rod per warp.  Lane-exact numpy model of stage 1: tools/dmma_gj_emulator.py.
+//
+// Replaces, per rod, the same reference code as sri_fused16.cuh (updateA main.cpp:55-88, A_NN.inverse()*(b-ivp)
+// main.cpp:113, updatePositionb main.cpp:121-140, Dn_NN_inv*(b_NN-ivp) main.cpp:172) plus rod_modeling.pdf 1.17-1.18.
+//
+// Why: in the scalar kernel a row lives in one lane and the pivot row has to be broadcast through the LSU, which is
+// what bounds it.  The DMMA data path does that broadcast for free.  The M x M quaternion system
+//      sum_j Q_j (x) c_ij = b_i
+// is stored as the REAL 64 x 16 matrix  Cr[4 i + r][j] = component r of c_ij  (column 15 = b_i), i.e. 8 x 2 DMMA
+// accumulator tiles of 8 x 8 = 32 doubles per lane.  With vec(a (x) b) = Rmat(b) vec(a), Gauss-Jordan step k is
+//      U'  = Rmat(c_kk^-1) U            U = pivot row as a 4 x 16 matrix (one DMMA per column tile)
+//      Cr -= [Rmat(c_0k); Rmat(c_1k); ...; Rmat(c_kk - 1); ...] U'      (rank-4 update: 8 x 2 DMMAs, k = 4 exactly)
+// 4 x 4 real blocks appear only in the A operand (the multipliers); the matrix itself stays in quaternion (4-vector)
+// form, so the DMMAs execute exactly the 16 FMAs per quaternion multiply-add of the scalar kernel.
+// Per step the LSU only moves the pivot row into B-fragment layout (2 SHFL.64 per column tile), the pivot element
+// to every lane (4 SHFL.64) and the pivot column into A-fragment layout (1 SHFL.64 per row tile).
+//
+// Pivoting: the order is static (pivot k = row k).  The left-preconditioned operator I - 1/2 S diag(kappa) has
+// |c_kk| >= 1 and measured sub-diagonal growth <= 0.15 for |K| <= 10 and <= 2.4 for |K| <= 300, so a search would
+// almost never move a row.  Every step still checks  max_{i>k} |c_ik| <= G |c_kk|  (and c_kk != 0); a rod that
+// fails is appended to a list and re-solved by the row-pivoting scalar kernel (sri_fused16.cuh) right after.
+#pragma once
+#include "sri_fused16.cuh"
+#include "sri_stage_dmma.cuh"
+
+namespace sri {
+
+#ifndef SRI_DMMA_MINBLOCKS
+#define SRI_DMMA_MINBLOCKS 4
+#endif
+constexpr int kDmmaThreads = 128;
+constexpr double kDmmaGrowthDefault = 4.0;  // accepted max_{i>k} |c_ik| / |c_kk| (SRI_DMMA_GROWTH overrides)
+
+// Table appended to the StageTables block: Stx[i][j] (row-major 16 x 16) = -1/2 (Dn_NN^-1)(i,j) for i, j < M,
+// Stx[i][15] = g_i = -(Dn_NN^-1 Dn_IN)_i, zero elsewhere.
+struct DmmaTables {
+    static constexpr int Stx = StageTables::total;
+    static constexpr int total = Stx + 256;
+};
+
+// Per-warp shared scratch (doubles)
+struct DmmaScratch {
+    static constexpr int kx = 0;                // [2][4][16] (double buffered): row 0 = (0,..,0,q0w), rows 1..3 = (K_c[0..M-1], 0.., q0_c)
+    static constexpr int fbar = kx + 128;       // [3][16]
+    static constexpr int lbar = fbar + 48;      // [3][16]
+    static constexpr int gam = lbar + 48;       // [3][16]
+    static constexpr int misc = gam + 48;       // [16]: F_tip 0..2, M_tip 4..6, r0 8..10
+    static constexpr int qnode = misc + 16;     // [16][4] quaternions by node (slot M = base node)
+    static constexpr int vec = qnode + 64;      // [16][4] r' by node
+    static constexpr int vec2 = vec + 64;       // [16][4] right-hand sides of stages 3, 4 by reduced row
+    static constexpr int total = vec2 + 64;     // 480 doubles
+};
+constexpr size_t kDmmaSmem = (OpsLayout16::total + 256 + (kDmmaThreads / 32) * DmmaScratch::total) * sizeof(double);
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double dmma_zero(double a, double b) {  // column 0/2/4/6 of A*B (C fragment register 0)
+    double d0, d1;
+    const double z = 0.0;
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(z));
+    (void)d1;
+    return d0;
+}
+__device__ __forceinline__ double flip_sign(double v, unsigned mask) {
+    return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+}
+
+// out_c (c = 0..2) = sum over this lane's half of the columns j of T[j*16+row] * v[j][c]; the two halves are added
+// by one xor-16 shuffle.  T has 15 columns (j = 15 does not exist); v rows are zero beyond the rod.
+__device__ __forceinline__ void contract_halves(const double* T, const double* v, int row, int half, double& o0,
+                                                double& o1, double& o2) {
+    double a[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const int j = 8 * half + jj;
+        if (j < 15) {
+            const double t = T[j * MP16 + row];
+            const double2 v01 = *reinterpret_cast<const double2*>(v + 4 * j);
+            const double v2 = v[4 * j + 2];
+            a[jj & 1][0] = fma(t, v01.x, a[jj & 1][0]);
+            a[jj & 1][1] = fma(t, v01.y, a[jj & 1][1]);
+            a[jj & 1][2] = fma(t, v2, a[jj & 1][2]);
+        }
+    }
+    o0 = a[0][0] + a[1][0]; o1 = a[0][1] + a[1][1]; o2 = a[0][2] + a[1][2];
+    o0 += __shfl_xor_sync(0xffffffffu, o0, 16);
+    o1 += __shfl_xor_sync(0xffffffffu, o1, 16);
+    o2 += __shfl_xor_sync(0xffffffffu, o2, 16);
+}
+
+template <int MS>
+__global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma_kernel(const FusedParams p) {
+    extern __shared__ __align__(16) double smem[];
+    double* tab = smem;                        // OpsLayout16::total doubles (Sp, STt, g, gT, DTI used here)
+    double* stx = smem + OpsLayout16::total;   // 256 doubles
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* scr = stx + 256 + warp * DmmaScratch::total;
+    double* qnode = scr + DmmaScratch::qnode;
+    double* vec = scr + DmmaScratch::vec;
+    double* vec2 = scr + DmmaScratch::vec2;
+    double* misc = scr + DmmaScratch::misc;
+
+    constexpr int kWarps = kDmmaThreads / 32;
+    if ((long long)blockIdx.x * kWarps >= p.batch) return;  // whole CTA idle
+    for (int i = threadIdx.x; i < OpsLayout16::total; i += kDmmaThreads) tab[i] = p.ops[i];
+    for (int i = threadIdx.x; i < 256; i += kDmmaThreads) stx[i] = p.ops[DmmaTables::Stx + i];
+    for (int i = lane; i < DmmaScratch::total; i += 32) scr[i] = 0.0;
+    __syncthreads();
+
+    const int M = MS ? MS : p.M;
+    const int N = M + 1;
+    // fragment coordinates of this lane
+    const int rho = lane >> 2, cp = lane & 3;  // C fragment: row rho, columns 2cp, 2cp+1
+    const int hi = rho >> 2, rr = rho & 3;     // quaternion row within the tile, component
+    // stage coordinates
+    const int row = lane & 15, half = lane >> 4;
+
+    // lane constants of the elimination (see tools/dmma_gj_emulator.py)
+    const int srcU_base = 4 * cp + (lane >> 3);
+    const bool odd_col = (rho & 1) != 0;
+    const int srcL_base = 16 * hi + 4 * (rr ^ cp);
+    // Rmat(b)[r][s] = sg(r,s) b[r^s]: rows (+,-,-,-), (+,+,+,-), (+,-,+,+), (+,+,-,+)
+    const unsigned neg_tab = 0x428Eu;  // bit (4r+s) set where sg(r,s) = -1: r0: s1,s2,s3; r1: s3; r2: s1; r3: s2
+    const unsigned sgL_mask = ((neg_tab >> (4 * rr + cp)) & 1u) << 31;
+    const double dpiv0 = (hi == 0 && rr == cp) ? 1.0 : 0.0;
+    const double dpiv1 = (hi == 1 && rr == cp) ? 1.0 : 0.0;
+    const unsigned hi_mask = hi ? 0x7fffffffu : 0u;
+    // normalisation operand: B[q = cp][n = rho]; even n = 2 s' carries -Rmat(c^-1)[s'][q] = -sg(s',q) conj(c)[s'^q] / |c|^2
+    const int sp = rho >> 1;
+    const int idxN = sp ^ cp;
+    double sgN = 0.0;
+    if (!odd_col) {
+        const bool neg_rm = ((neg_tab >> (4 * sp + cp)) & 1u) != 0;
+        const bool neg_conj = idxN != 0;
+        sgN = (neg_rm != neg_conj) ? 1.0 : -1.0;  // -(sg * conj)
+    }
+    // identity entries of the assembly: tile (t, ct), register e holds delta_ij iff rr == 0, hi == e, cp == t - 4 ct
+    const int diag_code = (rr == 0) ? (4 * hi + cp) : -1;
+
+    const long long stride = (long long)gridDim.x * kWarps;
+    const long long rod0 = (long long)blockIdx.x * kWarps + warp;
+
+    // strain samples and q0 of rod `rod_` -> kx[slot]
+    auto prefetch_K = [&](long long rod_, int slot) {
+        double* kb = scr + DmmaScratch::kx + slot * 64;
+        if (row < M) {
+            const double* s = p.K + rod_ * 3 * N + row;
+            if (half == 0) { cp_async8(kb + 16 + row, s); cp_async8(kb + 32 + row, s + N); }
+            else cp_async8(kb + 48 + row, s + 2 * N);
+        }
+        if (lane < 4) {
+            if (p.q0) cp_async8(kb + 16 * lane + 15, p.q0 + rod_ * 4 + lane);
+            else kb[16 * lane + 15] = (lane == 0) ? 1.0 : 0.0;
+        }
+    };
+
+    if (rod0 < p.batch) prefetch_K(rod0, 0);
+    cp_async_commit();
+
+    int it = 0;
+    for (long long rod = rod0; rod < p.batch; rod += stride, ++it) {
+        const int cur = it & 1;
+        // ---- prefetch: this rod's late inputs and the next rod's strain samples --------------------------------
+        if (row < N) {
+            const int c0 = half ? 2 : 0, c1 = half ? 3 : 2;  // half 0: components 0, 1; half 1: component 2
+            for (int c = c0; c < c1; ++c) {
+                if (p.fbar) cp_async8(scr + DmmaScratch::fbar + 16 * c + row, p.fbar + (rod * 3 + c) * N + row);
+                if (p.lbar) cp_async8(scr + DmmaScratch::lbar + 16 * c + row, p.lbar + (rod * 3 + c) * N + row);
+                if (p.Gamma) cp_async8(scr + DmmaScratch::gam + 16 * c + row, p.Gamma + (rod * 3 + c) * N + row);
+            }
+        }
+        if (lane < 3) { if (p.F_tip) cp_async8(misc + lane, p.F_tip + rod * 3 + lane); }
+        else if (lane >= 4 && lane < 7) { if (p.M_tip) cp_async8(misc + lane, p.M_tip + rod * 3 + lane - 4); }
+        else if (lane >= 8 && lane < 11) { if (p.r0) cp_async8(misc + lane, p.r0 + rod * 3 + lane - 8); }
+        if (rod + stride < p.batch) prefetch_K(rod + stride, cur ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed: this rod's K and q0 have landed
+        __syncwarp();
+
+        const double* kb = scr + DmmaScratch::kx + cur * 64;
+        // ---- stage 1: assemble Cr = delta - 1/2 S_ij (0,K_j) | g_i q0 in C-fragment layout -------------------------
+        double c[8][2][2];
+        {
+            double kq[2][2];
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                const double2 v = *reinterpret_cast<const double2*>(kb + 16 * rr + 8 * ct + 2 * cp);
+                kq[ct][0] = v.x; kq[ct][1] = v.y;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    const double2 s = *reinterpret_cast<const double2*>(stx + (2 * t + hi) * 16 + 8 * ct + 2 * cp);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int dcode = 4 * e + (t - 4 * ct);  // compile-time
+                        const bool candidate = (t - 4 * ct >= 0) && (t - 4 * ct < 4) && !(ct == 1 && t == 7 && e == 1);
+                        const double d = (candidate && diag_code == dcode) ? 1.0 : 0.0;
+                        c[t][ct][e] = fma(e ? s.y : s.x, kq[ct][e], d);
+                    }
+                }
+        }
+        // ---- Gauss-Jordan over the quaternions on DMMA, static pivot order -------------------------------------
+        bool bad = false;
+        const double growth2 = p.growth2;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+            if (MS == 0 && k >= M) break;
+            const int kt = k >> 1, kh = k & 1, kc = k >> 3, kcp = (k & 7) >> 1, ke = k & 1;
+            // 1. pivot row -> B fragments: lane wants U[s = cp][col = 8 ct + rho]
+            const int srcU = 16 * kh + srcU_base;
+            double ub[2];
+#pragma unroll
+            for (int ct = kc; ct < 2; ++ct) {
+                const double v0 = __shfl_sync(0xffffffffu, c[kt][ct][0], srcU);
+                const double v1 = __shfl_sync(0xffffffffu, c[kt][ct][1], srcU);
+                ub[ct] = odd_col ? v1 : v0;
+            }
+            // 2. pivot element c_kk to every lane, its inverse into the normalisation operand
+            const int pl = 4 * (k & 7);
+            const double pc0 = __shfl_sync(0xffffffffu, ub[kc], pl);
+            const double pc1 = __shfl_sync(0xffffffffu, ub[kc], pl + 1);
+            const double pc2 = __shfl_sync(0xffffffffu, ub[kc], pl + 2);
+            const double pc3 = __shfl_sync(0xffffffffu, ub[kc], pl + 3);
+            const double nrm = fma(pc0, pc0, pc1 * pc1) + fma(pc2, pc2, pc3 * pc3);
+            const double inv = fast_rcp(nrm);
+            const double pcsel = (idxN & 2) ? ((idxN & 1) ? pc3 : pc2) : ((idxN & 1) ? pc1 : pc0);
+            const double bn = (sgN * inv) * pcsel;
+            // 3. pivot column -> A fragments Rmat(c_ik) (all row tiles, before anything is updated) + growth check
+            const int srcL = srcL_base + kcp;
+            double la[8];
+            unsigned mx = 0u;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const double v = __shfl_sync(0xffffffffu, c[t][kc][ke], srcL);
+                const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
+                if (t > kt) mx = max(mx, h);
+                else if (t == kt && kh == 0) mx = max(mx, h & hi_mask);
+                la[t] = flip_sign(v, sgL_mask);
+            }
+            la[kt] -= kh ? dpiv1 : dpiv0;  // pivot row: Rmat(c_kk - 1) leaves exactly the normalised row
+            {
+                const double x = __hiloint2double((int)mx, 0);
+                bad = bad || !(x * x <= growth2 * nrm) || !(nrm > 1e-280);
+            }
+            // 4. normalise the pivot row (negated) and 5. rank-4 update of every row tile
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                if (8 * ct + 7 > k) {
+                    const double un = dmma_zero(ub[ct], bn);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) dmma(c[t][ct][0], c[t][ct][1], la[t], un);
+                }
+            }
+        }
+        const bool flagged = __any_sync(0xffffffffu, bad);
+        cp_async_wait<0>();
+        if (flagged && p.rod_list) {
+            // this rod needs row pivoting: hand it to the scalar kernel
+            if (lane == 0) p.rod_list[atomicAdd(p.rod_count, 1)] = (int)rod;
+            __syncwarp();
+            continue;
+        }
+        // ---- the solution is column 15: lanes cp == 3, register [t][1][1] -> qnode[i][r] ----------------------
+        if (cp == 3) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) qnode[4 * (2 * t + hi) + rr] = c[t][1][1];
+        }
+        __syncwarp();
+        if (lane < 4) qnode[4 * M + lane] = kb[16 * lane + 15];  // base node: q0
+        if (p.info && lane == 0) p.info[rod] = flagged ? -1 : 0;
+        __syncwarp();
+        quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+        if (row <= M) q = ld_quat(qnode + 4 * row);
+        if (p.Q && row < M) {
+            double* d = p.Q + rod * 4 * M + (2 * half) * M + row;
+            d[0] = half ? q.y : q.w;
+            d[M] = half ? q.z : q.x;
+        }
+
+        if (p.r || p.n || p.m) {
+            // ---- stage 2: r = S (R(q) Gamma) + g r0 ----------------------------------------------------------
+            double bv0 = 0.0, bv1 = 0.0, bv2 = 0.0;
+            if (row <= M) {
+                if (p.Gamma) {
+                    const double* gm = scr + DmmaScratch::gam + row;
+                    q_rotate(q, gm[0], gm[16], gm[32], bv0, bv1, bv2);
+                } else {
+                    q_rotate_e1(q, bv0, bv1, bv2);
+                }
+            }
+            if (half == 0) { quat t; t.w = bv0; t.x = bv1; t.y = bv2; t.z = 0.0; st_quat(vec + 4 * row, t); }
+            // ---- stage 3 right-hand side --------------------------------------------------------------------
+            double F0 = 0.0, F1 = 0.0, F2 = 0.0;
+            if ((p.n || p.m) && p.F_tip) { F0 = misc[0]; F1 = misc[1]; F2 = misc[2]; }
+            const bool contract3 = (p.n || p.m) && p.fbar;
+            if (contract3 && half == 1) {
+                const double dti = tab[OpsLayout16::DTI + row];
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+                if (row < M) { const double* s = scr + DmmaScratch::fbar + row + 1; f0 = s[0]; f1 = s[16]; f2 = s[32]; }
+                quat t; t.w = -f0 - dti * F0; t.x = -f1 - dti * F1; t.y = -f2 - dti * F2; t.z = 0.0;
+                st_quat(vec2 + 4 * row, t);
+            }
+            __syncwarp();
+            if (p.r) {
+                double a0, a1, a2;
+                contract_halves(tab + OpsLayout16::Sp, vec, row, half, a0, a1, a2);
+                if (p.r0) {
+                    const double gi = tab[OpsLayout16::g + row];
+                    a0 = fma(gi, misc[8], a0); a1 = fma(gi, misc[9], a1); a2 = fma(gi, misc[10], a2);
+                }
+                if (row < M) {
+                    double* d = p.r + rod * 3 * M + row;
+                    if (half == 0) { d[0] = a0; d[M] = a1; } else d[2 * M] = a2;
+                }
+            }
+            if (p.n || p.m) {
+                // ---- stage 3: n = D_TT^-1 (-fbar - D_TI F_tip^T); lane `row` = reduced index (node row+1) --------
+                double n0, n1, n2;
+                if (contract3) {
+                    contract_halves(tab + OpsLayout16::STt, vec2, row, half, n0, n1, n2);
+                } else {
+                    const double gi = tab[OpsLayout16::gT + row];
+                    n0 = gi * F0; n1 = gi * F1; n2 = gi * F2;
+                }
+                if (p.n && row < M) {
+                    double* d = p.n + rod * 3 * M + row;
+                    if (half == 0) { d[0] = n0; d[M] = n1; } else d[2 * M] = n2;
+                }
+                if (p.m) {
+                    // ---- stage 4: m = D_TT^-1 (-(r' x n + lbar) - D_TI M_tip^T) ------------------------------
+                    const double T0 = misc[4], T1 = misc[5], T2 = misc[6];
+                    const int nb = (row < M) ? row + 1 : row;  // node of this reduced row
+                    const double2 rp01 = *reinterpret_cast<const double2*>(vec + 4 * nb);
+                    const double rp2 = vec[4 * nb + 2];
+                    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+                    if (p.lbar && row < M) { const double* s = scr + DmmaScratch::lbar + row + 1; l0 = s[0]; l1 = s[16]; l2 = s[32]; }
+                    const double dti = tab[OpsLayout16::DTI + row];
+                    const double x0 = rp01.y * n2 - rp2 * n1, x1 = rp2 * n0 - rp01.x * n2, x2 = rp01.x * n1 - rp01.y * n0;
+                    quat t; t.w = -(x0 + l0) - dti * T0; t.x = -(x1 + l1) - dti * T1; t.y = -(x2 + l2) - dti * T2; t.z = 0.0;
+                    if (row >= M) { t.w = 0.0; t.x = 0.0; t.y = 0.0; }
+                    __syncwarp();  // every lane has read vec2 (stage 3) before it is overwritten
+                    if (half == 0) st_quat(vec2 + 4 * row, t);
+                    __syncwarp();
+                    double m0, m1, m2;
+                    contract_halves(tab + OpsLayout16::STt, vec2, row, half, m0, m1, m2);
+                    if (row < M) {
+                        double* d = p.m + rod * 3 * M + row;
+                        if (half == 0) { d[0] = m0; d[M] = m1; } else d[2 * M] = m2;
+                    }
+                }
+            }
+        }
+        __syncwarp();  // scratch is reused by the next iteration
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace sri

@@ -159,6 +159,11 @@ int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t ba
 const char* sri_last_error_string(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t sri_kernel_launch_count(void);
+/* N <= 16: the elimination runs on the FP64 tensor cores in static pivot order; a rod whose sub-diagonal growth
+ * max_{i>k} |c_ik| / |c_kk| exceeds the accepted bound (4; environment SRI_DMMA_GROWTH at sri_create) is handed
+ * back to the row-pivoting kernel inside the same call.  Returns how many rods of the most recent device-buffer
+ * call on this handle took that second pass (synchronises the handle's stream).  0 for N > 16. */
+int sri_get_handback_count(sri_handle h, int64_t* count);
 /* Runs the library's FP64 FMA peak probe on the handle's device and returns TFLOP/s (roofline denominator). */
 int sri_measure_fp64_peak(sri_handle h, double* tflops);
 

@@ -155,6 +155,75 @@ def test_large_curvature_needs_pivoting(h16, oracle16, torch_mod):
         assert rel_err(got[s], ref[s]) <= 1e-10, s
 
 
+def _handle_with_env(monkeypatch, **env):
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    h = SpectralRodIntegrator(16, 0)  # the environment is read by sri_create
+    for k in env:
+        monkeypatch.delenv(k)
+    return h
+
+
+def test_dmma_elimination_takes_no_second_pass_on_benchmark_rods(h16, oracle16, torch_mod):
+    """Default path for N <= 16: static-order elimination on the FP64 tensor cores.  On the SURVEY 8(d) strain range the
+    growth check never fires, so every rod is solved by the DMMA kernel alone."""
+    K, F, Mt, fb = oracle16.generate_rods(0x5EED, 5000, 4000)
+    got = _gpu_all(h16, torch_mod, K, F, Mt, fbar=fb)
+    assert h16.handback_count() == 0
+    ref = oracle16.integrate_all(K, F, Mt, fbar=fb)
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, s
+
+
+@pytest.mark.parametrize("growth,expect", [("0", "all"), ("0.01", "some")])
+def test_dmma_hands_rods_back_to_the_pivoting_kernel(monkeypatch, sri_lib, oracle16, torch_mod, growth, expect):
+    """A rod whose sub-diagonal growth exceeds the bound is re-solved by the row-pivoting scalar kernel in the same call.
+    Forced here with a tiny bound: results must equal the all-scalar run bit for bit on the handed-back rods and agree
+    with the oracle everywhere."""
+    B = 3001
+    K, F, Mt, fb = oracle16.generate_rods(0x5EED, 77, B)
+    ref = oracle16.integrate_all(K, F, Mt, fbar=fb)
+    hs = _handle_with_env(monkeypatch, SRI_FUSED16_IMPL="scalar")
+    hd = _handle_with_env(monkeypatch, SRI_DMMA_GROWTH=growth)
+    try:
+        scalar = _gpu_all(hs, torch_mod, K, F, Mt, fbar=fb)
+        assert hs.handback_count() == 0
+        got = _gpu_all(hd, torch_mod, K, F, Mt, fbar=fb)
+        nback = hd.handback_count()
+    finally:
+        hs.close(); hd.close()
+    assert (got["info"] == 0).all() and (scalar["info"] == 0).all()
+    if expect == "all":
+        assert nback == B
+        for s in "Qrnm":
+            assert np.array_equal(got[s], scalar[s]), s
+    else:
+        assert 0 < nback < B, nback
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, s
+        assert rel_err(scalar[s], ref[s]) <= TOL, s
+
+
+def test_large_curvature_static_order_vs_pivoting(monkeypatch, sri_lib, oracle16, torch_mod):
+    """|K| up to ~500 (far beyond any resolvable rod): whichever kernel ends up solving a rod, the result agrees with the
+    scalar row-pivoting kernel to the accuracy cond(A_NN) eps allows."""
+    rng = np.random.default_rng(11)
+    B = 1500
+    K = rng.uniform(-300, 300, size=(B, 3, 1)) + rng.uniform(-200, 200, size=(B, 3, 1)) * np.linspace(1, -1, 16)[None, None, :]
+    F = rng.uniform(-1, 1, size=(B, 3)); Mt = rng.uniform(-1, 1, size=(B, 3))
+    hs = _handle_with_env(monkeypatch, SRI_FUSED16_IMPL="scalar")
+    hd = _handle_with_env(monkeypatch)
+    try:
+        scalar = _gpu_all(hs, torch_mod, K, F, Mt)
+        got = _gpu_all(hd, torch_mod, K, F, Mt)
+    finally:
+        hs.close(); hd.close()
+    assert (got["info"] == 0).all()
+    for s in "Qrnm":
+        assert rel_err(got[s], scalar[s]) <= 1e-9, s
+
+
 def test_shape_residual(h16, oracle16, torch_mod):
     B = 400
     K, F, Mt, fb = oracle16.generate_rods(21, 0, B)
