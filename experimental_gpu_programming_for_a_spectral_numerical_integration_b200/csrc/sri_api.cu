@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -375,7 +376,11 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
         if (h->use_dmma) {
             if (p.batch > 0x7fffffffLL) return fail(SRI_ERR_INVALID_ARGUMENT, "batch too large for one call (2^31 rods)");
             SRI_TRY(list_reserve(h, list_slot, p.batch));
-            p.growth2 = h->dmma_growth * h->dmma_growth;
+            {
+                const double g2 = h->dmma_growth * h->dmma_growth;
+                const double lg = (g2 > 0.0) ? std::log2(g2) * 1048576.0 : -2.0e9;
+                p.growth_log = (int)std::lround(std::max(-2.0e9, std::min(2.0e9, lg)));
+            }
             p.rod_count = h->d_list[list_slot];
             p.rod_list = h->d_list[list_slot] + 4;
             SRI_CUDA(cudaMemsetAsync(p.rod_count, 0, sizeof(int), stream));

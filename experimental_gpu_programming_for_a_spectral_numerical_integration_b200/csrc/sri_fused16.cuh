@@ -66,7 +66,7 @@ struct FusedParams {
     // which in that mode integrates rods rod_list[0 .. *rod_count) instead of 0 .. batch.
     int* rod_list;
     int* rod_count;
-    double growth2;  // DMMA kernel: square of the accepted sub-diagonal growth max_{i>k} |c_ik| / |c_kk|
+    int growth_log;  // DMMA kernel: 2^20 log2(G^2), G = accepted sub-diagonal growth max_{i>k} |c_ik| / |c_kk|
 };
 
 // Per-rod shared scratch (doubles).

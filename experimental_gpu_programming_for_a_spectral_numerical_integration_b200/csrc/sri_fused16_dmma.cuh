@@ -29,7 +29,10 @@ namespace sri {
 #ifndef SRI_DMMA_MINBLOCKS
 #define SRI_DMMA_MINBLOCKS 4
 #endif
-constexpr int kDmmaThreads = 128;
+#ifndef SRI_DMMA_THREADS
+#define SRI_DMMA_THREADS 128
+#endif
+constexpr int kDmmaThreads = SRI_DMMA_THREADS;
 constexpr double kDmmaGrowthDefault = 4.0;  // accepted max_{i>k} |c_ik| / |c_kk| (SRI_DMMA_GROWTH overrides)
 
 // Table appended to the StageTables block: Stx[i][j] (row-major 16 x 16) = -1/2 (Dn_NN^-1)(i,j) for i, j < M,
@@ -91,7 +94,11 @@ __device__ __forceinline__ void contract_halves(const double* T, const double* v
 }
 
 template <int MS>
+#ifdef SRI_DMMA_MAXNREG
+__global__ void __maxnreg__(SRI_DMMA_MAXNREG) fused16_dmma_kernel(const FusedParams p) {
+#else
 __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma_kernel(const FusedParams p) {
+#endif
     extern __shared__ __align__(16) double smem[];
     double* tab = smem;                        // OpsLayout16::total doubles (Sp, STt, g, gT, DTI used here)
     double* stx = smem + OpsLayout16::total;   // 256 doubles
@@ -130,12 +137,8 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
     // normalisation operand: B[q = cp][n = rho]; even n = 2 s' carries -Rmat(c^-1)[s'][q] = -sg(s',q) conj(c)[s'^q] / |c|^2
     const int sp = rho >> 1;
     const int idxN = sp ^ cp;
-    double sgN = 0.0;
-    if (!odd_col) {
-        const bool neg_rm = ((neg_tab >> (4 * sp + cp)) & 1u) != 0;
-        const bool neg_conj = idxN != 0;
-        sgN = (neg_rm != neg_conj) ? 1.0 : -1.0;  // -(sg * conj)
-    }
+    // sign of -(sg(s',q) conj): negative iff sg and conj have the same sign
+    const unsigned sgN_mask = ((((neg_tab >> (4 * sp + cp)) & 1u) != 0) == (idxN != 0)) ? 0x80000000u : 0u;
     // identity entries of the assembly: tile (t, ct), register e holds delta_ij iff rr == 0, hi == e, cp == t - 4 ct
     const int diag_code = (rr == 0) ? (4 * hi + cp) : -1;
 
@@ -203,67 +206,86 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                     }
                 }
         }
-        // ---- Gauss-Jordan over the quaternions on DMMA, static pivot order -------------------------------------
+        // ---- Gauss-Jordan over the quaternions on DMMA, static pivot order, software pipelined -----------------
+        // Iteration k issues the rank-4 update of step k and, behind it, everything step k+1 needs: its tile row is
+        // updated first, then the next pivot row / pivot element are gathered and the reciprocal chain (the only serial
+        // scalar FP64 work) runs while the other 14 DMMAs of step k go through the pipe; each la[t] is re-gathered
+        // for step k+1 as soon as tile row t has been updated.  k = -1 is the prologue (no update).
         bool bad = false;
-        const double growth2 = p.growth2;
+        const int growth_log = p.growth_log;
+        double la[8], un[2];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) {
-            if (MS == 0 && k >= M) break;
-            const int kt = k >> 1, kh = k & 1, kc = k >> 3, kcp = (k & 7) >> 1, ke = k & 1;
-            // 1. pivot row -> B fragments: lane wants U[s = cp][col = 8 ct + rho]
-            const int srcU = 16 * kh + srcU_base;
-            double ub[2];
+        for (int k = -1; k < 15; ++k) {
+            const int kn = k + 1;  // the step being prepared
+            const bool upd = (k >= 0) && (MS != 0 || k < M);
+            const bool prep = (kn < 15) && (MS != 0 || kn < M);
+            const int nt = (kn >> 1) & 7, nh = kn & 1, nc = (kn >> 3) & 1, ncp = (kn & 7) >> 1, ne = kn & 1;
+            // 1. step k on the tile row of the next pivot
+            if (upd) {
 #pragma unroll
-            for (int ct = kc; ct < 2; ++ct) {
-                const double v0 = __shfl_sync(0xffffffffu, c[kt][ct][0], srcU);
-                const double v1 = __shfl_sync(0xffffffffu, c[kt][ct][1], srcU);
-                ub[ct] = odd_col ? v1 : v0;
+                for (int ct = 0; ct < 2; ++ct)
+                    if (8 * ct + 7 > k) dmma(c[nt][ct][0], c[nt][ct][1], la[nt], un[ct]);
             }
-            // 2. pivot element c_kk to every lane, its inverse into the normalisation operand
-            const int pl = 4 * (k & 7);
-            const double pc0 = __shfl_sync(0xffffffffu, ub[kc], pl);
-            const double pc1 = __shfl_sync(0xffffffffu, ub[kc], pl + 1);
-            const double pc2 = __shfl_sync(0xffffffffu, ub[kc], pl + 2);
-            const double pc3 = __shfl_sync(0xffffffffu, ub[kc], pl + 3);
-            const double nrm = fma(pc0, pc0, pc1 * pc1) + fma(pc2, pc2, pc3 * pc3);
-            const double inv = fast_rcp(nrm);
-            const double pcsel = (idxN & 2) ? ((idxN & 1) ? pc3 : pc2) : ((idxN & 1) ? pc1 : pc0);
-            const double bn = (sgN * inv) * pcsel;
-            // 3. pivot column -> A fragments Rmat(c_ik) (all row tiles, before anything is updated) + growth check
-            const int srcL = srcL_base + kcp;
-            double la[8];
+            double un0[2] = {0.0, 0.0}, r0 = 0.0, t2 = 0.0;
             unsigned mx = 0u;
+            int thr = 0;
+            if (prep) {
+                // next pivot row -> B fragments: lane wants U[s = cp][col = 8 ct + rho]
+                const int srcU = 16 * nh + srcU_base;
+                // this lane's entry of -Rmat(conj c_kk) (operand of the normalisation; odd columns are don't-care)
+                const double pcs = __shfl_sync(0xffffffffu, c[nt][nc][ne], 16 * nh + 4 * idxN + ncp);
+                const double bn0 = flip_sign(pcs, sgN_mask);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const double v = __shfl_sync(0xffffffffu, c[t][kc][ke], srcL);
-                const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
-                if (t > kt) mx = max(mx, h);
-                else if (t == kt && kh == 0) mx = max(mx, h & hi_mask);
-                la[t] = flip_sign(v, sgL_mask);
-            }
-            la[kt] -= kh ? dpiv1 : dpiv0;  // pivot row: Rmat(c_kk - 1) leaves exactly the normalised row
-            {
-                const double x = __hiloint2double((int)mx, 0);
-                bad = bad || !(x * x <= growth2 * nrm) || !(nrm > 1e-280);
-            }
-            // 4. normalise the pivot row (negated) and 5. rank-4 update of every row tile
-#pragma unroll
-            for (int ct = 0; ct < 2; ++ct) {
-                if (8 * ct + 7 > k) {
-                    const double un = dmma_zero(ub[ct], bn);
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) dmma(c[t][ct][0], c[t][ct][1], la[t], un);
+                for (int ct = nc; ct < 2; ++ct) {
+                    const double v0 = __shfl_sync(0xffffffffu, c[nt][ct][0], srcU);
+                    const double v1 = __shfl_sync(0xffffffffu, c[nt][ct][1], srcU);
+                    un0[ct] = dmma_zero(odd_col ? v1 : v0, bn0);  // -U (x) conj(c_kk), B-fragment layout
                 }
+                // its (column k, w) entry is -|c_kk|^2: one shuffle instead of a scalar FP64 reduction, so that the
+                // serial chain on the (shared, DMMA-loaded) FP64 pipe is DMMA -> e -> t2 -> scale
+                const double nu = -__shfl_sync(0xffffffffu, un0[nc], 4 * (kn & 7));
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(nu));
+                const double e = fma(-nu, r0, 1.0);
+                t2 = fma(e, e, e);  // 1/nu = r0 (1 + e + e^2) to ~1e-16
+                // growth bound in the log domain (hi word of a positive double ~ 2^20 (log2 + 1023)):
+                //   |c_ik| <= G |c_kk|  <=>  2 H(|c_ik|) <= H(nu) + (1023 << 20) + 2^20 log2(G^2)
+                const int hn = __double2hiint(nu);
+                thr = (int)(((long long)hn + 0x3ff00000LL + (long long)growth_log) >> 1);
+                if (hn < 0x05000000 || hn >= 0x7ff00000) thr = -1;  // zero / tiny / negative / inf / NaN pivot norm
+            }
+            // 2. step k on the other tile rows; la[t] is re-gathered for step k+1 once tile row t is done
+            const int srcL = srcL_base + ncp;
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+                const int t = (nt + tt) & 7;  // the next pivot's tile row first (already updated above)
+                if (upd && tt != 0) {
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+                        if (8 * ct + 7 > k) dmma(c[t][ct][0], c[t][ct][1], la[t], un[ct]);
+                }
+                if (prep) {
+                    const double v = __shfl_sync(0xffffffffu, c[t][nc][ne], srcL);
+                    const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
+                    if (t > nt) mx = max(mx, h);
+                    else if (t == nt && nh == 0) mx = max(mx, h & hi_mask);
+                    la[t] = flip_sign(v, sgL_mask);
+                    if (tt == 0) la[t] -= nh ? dpiv1 : dpiv0;  // pivot row: Rmat(c_kk - 1) leaves the normalised row
+                }
+            }
+            // 3. normalise the next pivot row (negated)
+            if (prep) {
+                bad = bad || ((int)mx > thr);
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+                    if (8 * ct + 7 > kn) { const double a = un0[ct] * r0; un[ct] = fma(a, t2, a); }
             }
         }
         const bool flagged = __any_sync(0xffffffffu, bad);
         cp_async_wait<0>();
-        if (flagged && p.rod_list) {
-            // this rod needs row pivoting: hand it to the scalar kernel
-            if (lane == 0) p.rod_list[atomicAdd(p.rod_count, 1)] = (int)rod;
-            __syncwarp();
-            continue;
-        }
+        // a flagged rod needs row pivoting: it is handed to the scalar kernel; its stores below are suppressed (no
+        // divergent `continue`, which would wrap every later shuffle in WARPSYNC/ENDCOLLECTIVE pairs)
+        const bool keep = !(flagged && p.rod_list);
+        if (!keep && lane == 0) p.rod_list[atomicAdd(p.rod_count, 1)] = (int)rod;
         // ---- the solution is column 15: lanes cp == 3, register [t][1][1] -> qnode[i][r] ----------------------
         if (cp == 3) {
 #pragma unroll
@@ -271,11 +293,11 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
         }
         __syncwarp();
         if (lane < 4) qnode[4 * M + lane] = kb[16 * lane + 15];  // base node: q0
-        if (p.info && lane == 0) p.info[rod] = flagged ? -1 : 0;
+        if (p.info && keep && lane == 0) p.info[rod] = flagged ? -1 : 0;
         __syncwarp();
         quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
         if (row <= M) q = ld_quat(qnode + 4 * row);
-        if (p.Q && row < M) {
+        if (p.Q && keep && row < M) {
             double* d = p.Q + rod * 4 * M + (2 * half) * M + row;
             d[0] = half ? q.y : q.w;
             d[M] = half ? q.z : q.x;
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                     const double gi = tab[OpsLayout16::g + row];
                     a0 = fma(gi, misc[8], a0); a1 = fma(gi, misc[9], a1); a2 = fma(gi, misc[10], a2);
                 }
-                if (row < M) {
+                if (keep && row < M) {
                     double* d = p.r + rod * 3 * M + row;
                     if (half == 0) { d[0] = a0; d[M] = a1; } else d[2 * M] = a2;
                 }
@@ -326,7 +348,7 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                     const double gi = tab[OpsLayout16::gT + row];
                     n0 = gi * F0; n1 = gi * F1; n2 = gi * F2;
                 }
-                if (p.n && row < M) {
+                if (p.n && keep && row < M) {
                     double* d = p.n + rod * 3 * M + row;
                     if (half == 0) { d[0] = n0; d[M] = n1; } else d[2 * M] = n2;
                 }
@@ -347,7 +369,7 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                     __syncwarp();
                     double m0, m1, m2;
                     contract_halves(tab + OpsLayout16::STt, vec2, row, half, m0, m1, m2);
-                    if (row < M) {
+                    if (keep && row < M) {
                         double* d = p.m + rod * 3 * M + row;
                         if (half == 0) { d[0] = m0; d[M] = m1; } else d[2 * M] = m2;
                     }

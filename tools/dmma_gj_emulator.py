@@ -85,12 +85,14 @@ def solve_rod(Stx, K, q0, M, growth=8.0):
             v0 = shfl(c[kt, ct, 0], src)
             v1 = shfl(c[kt, ct, 1], src)
             Ub[ct] = np.where((RHO & 1) == 1, v1, v0)
-        # 2. pivot element to every lane
-        pc = [shfl(Ub[kc], np.full(32, 4 * (k & 7) + q)) for q in range(4)]
-        nrm = pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2] + pc[3] * pc[3]
-        inv = 1.0 / nrm
-        pcsel = np.choose(idxN, pc)
-        bn = sgN * inv * pcsel
+        # 2. this lane's entry of -Rmat(conj c_kk), straight from the pivot's tile; un0 = -U (x) conj(c_kk) by DMMA;
+        #    its (column k, w) entry is -|c_kk|^2
+        pcs = shfl(c[kt, kc, ke], 16 * kh + 4 * idxN + kcp)
+        bn0 = sgN * pcs
+        un0 = {ct: mma_m8n8k4(np.zeros(32), np.zeros(32), Ub[ct], bn0)[0] for ct in Ub}
+        nu = -shfl(un0[kc], np.full(32, 4 * (k & 7)))
+        nrm = nu
+        inv = 1.0 / nu
         # 3. L fragments (column k of every row tile), before anything is updated
         srcL = srcL_base + kcp
         La = []
@@ -109,7 +111,7 @@ def solve_rod(Stx, K, q0, M, growth=8.0):
             flagged = True
         # 4. normalise the pivot row (negated), 5. update
         for ct in cts:
-            d0, _ = mma_m8n8k4(np.zeros(32), np.zeros(32), Ub[ct], bn)
+            d0 = un0[ct] * inv
             for t in range(8):
                 c[t, ct, 0], c[t, ct, 1] = mma_m8n8k4(c[t, ct, 0], c[t, ct, 1], La[t], d0)
     Q = np.zeros((16, 4))
