@@ -585,6 +585,17 @@ int sri_create(int N, int device, sri_handle* out) {
             for (int j = 0; j < M; ++j) t[sri::DmmaTables::Stx + i * 16 + j] = -0.5 * h->ops.S[j * M + i];
             t[sri::DmmaTables::Stx + i * 16 + 15] = h->ops.g[i];
         }
+        // stage operators in DMMA A-fragment order, boundary term as k index 15
+        for (int mt = 0; mt < 2; ++mt)
+            for (int kt = 0; kt < 4; ++kt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int i = 8 * mt + lane / 4, j = 4 * kt + lane % 4;
+                    double s = 0.0, tt = 0.0;
+                    if (i < M && j < M) { s = h->ops.S[j * M + i]; tt = -h->ops.ST[j * M + i]; }
+                    if (i < M && j == 15) { s = h->ops.g[i]; tt = h->ops.gT[i]; }
+                    t[sri::DmmaTables::AS + (mt * 4 + kt) * 32 + lane] = s;
+                    t[sri::DmmaTables::AT + (mt * 4 + kt) * 32 + lane] = tt;
+                }
         SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * sri::DmmaTables::total));
         SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * sri::DmmaTables::total, cudaMemcpyHostToDevice));
     } else {

@@ -35,26 +35,35 @@ namespace sri {
 constexpr int kDmmaThreads = SRI_DMMA_THREADS;
 constexpr double kDmmaGrowthDefault = 4.0;  // accepted max_{i>k} |c_ik| / |c_kk| (SRI_DMMA_GROWTH overrides)
 
-// Table appended to the StageTables block: Stx[i][j] (row-major 16 x 16) = -1/2 (Dn_NN^-1)(i,j) for i, j < M,
-// Stx[i][15] = g_i = -(Dn_NN^-1 Dn_IN)_i, zero elsewhere.
+// Tables appended to the StageTables block (all strain independent, built by sri_api.cu):
+//   Stx[i][j] (row-major 16 x 16) = -1/2 (Dn_NN^-1)(i,j) for i, j < M,  Stx[i][15] = g_i = -(Dn_NN^-1 Dn_IN)_i
+//   AS, AT: A fragments of the stage operators in DMMA fragment order, X[(mt*4 + kt)*32 + lane] =
+//           Xt[8 mt + lane/4][4 kt + lane%4], with the boundary term as k index 15:
+//           St[i][j<15] = (Dn_NN^-1)(i,j), St[i][15] = g_i;   Tt[i][j<15] = -(D_TT^-1)(i,j), Tt[i][15] = gT_i
 struct DmmaTables {
     static constexpr int Stx = StageTables::total;
-    static constexpr int total = Stx + 256;
+    static constexpr int AS = Stx + 256;
+    static constexpr int AT = AS + 256;
+    static constexpr int total = AT + 256;
 };
+constexpr int kDmmaTabDoubles = 768;  // Stx | AS | AT in shared memory
 
-// Per-warp shared scratch (doubles)
+// Per-warp shared scratch (doubles).  The [4][20] arrays hold a 3 x 16 right-hand side by (component, k index) with
+// the boundary value in k slot 15 and an all-zero fourth row (the unused columns of the B fragments); row stride 20
+// keeps the four rows on disjoint banks.
 struct DmmaScratch {
     static constexpr int kx = 0;                // [2][4][16] (double buffered): row 0 = (0,..,0,q0w), rows 1..3 = (K_c[0..M-1], 0.., q0_c)
-    static constexpr int fbar = kx + 128;       // [3][16]
-    static constexpr int lbar = fbar + 48;      // [3][16]
-    static constexpr int gam = lbar + 48;       // [3][16]
-    static constexpr int misc = gam + 48;       // [16]: F_tip 0..2, M_tip 4..6, r0 8..10
-    static constexpr int qnode = misc + 16;     // [16][4] quaternions by node (slot M = base node)
-    static constexpr int vec = qnode + 64;      // [16][4] r' by node
-    static constexpr int vec2 = vec + 64;       // [16][4] right-hand sides of stages 3, 4 by reduced row
-    static constexpr int total = vec2 + 64;     // 480 doubles
+    static constexpr int bs = kx + 128;         // [4][20] r' = R(q) Gamma at nodes 0..14 | r0
+    static constexpr int fbs = bs + 80;         // [4][20] fbar at nodes 1..15 (slot j = node j+1) | F_tip
+    static constexpr int xs = fbs + 80;         // [4][20] r' x n + lbar at nodes 1..15 | M_tip
+    static constexpr int rps = xs + 80;         // [3][16] r' at all 16 nodes
+    static constexpr int lbs = rps + 48;        // [3][16] lbar at nodes 1..15 (slot j = node j+1)
+    static constexpr int gam = lbs + 48;        // [3][16] Gamma by node
+    static constexpr int ns = gam + 48;         // [3][16] n by reduced row
+    static constexpr int qnode = ns + 48;       // [16][4] quaternions by node (slot M = base node)
+    static constexpr int total = qnode + 64;    // 624 doubles
 };
-constexpr size_t kDmmaSmem = (OpsLayout16::total + 256 + (kDmmaThreads / 32) * DmmaScratch::total) * sizeof(double);
+constexpr size_t kDmmaSmem = (kDmmaTabDoubles + (kDmmaThreads / 32) * DmmaScratch::total) * sizeof(double);
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -70,27 +79,28 @@ __device__ __forceinline__ double flip_sign(double v, unsigned mask) {
     return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
 }
 
-// out_c (c = 0..2) = sum over this lane's half of the columns j of T[j*16+row] * v[j][c]; the two halves are added
-// by one xor-16 shuffle.  T has 15 columns (j = 15 does not exist); v rows are zero beyond the rod.
-__device__ __forceinline__ void contract_halves(const double* T, const double* v, int row, int half, double& o0,
-                                                double& o1, double& o2) {
-    double a[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+// One cached-operator stage on the tensor cores: out[16 x 3] = At[16 x 16] * rhs[16 x 3], A fragments from the
+// fragment-ordered table `at`, B fragments from a [4][20] right-hand side (lane reads component min(rho,3), k = 4kt+cp).
+template <int KT0>
+__device__ __forceinline__ void stage_dmma16(const double* at, const double* rhs_lane, int lane, double (&acc)[2][2]) {
+    acc[0][0] = 0.0; acc[0][1] = 0.0; acc[1][0] = 0.0; acc[1][1] = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-        const int j = 8 * half + jj;
-        if (j < 15) {
-            const double t = T[j * MP16 + row];
-            const double2 v01 = *reinterpret_cast<const double2*>(v + 4 * j);
-            const double v2 = v[4 * j + 2];
-            a[jj & 1][0] = fma(t, v01.x, a[jj & 1][0]);
-            a[jj & 1][1] = fma(t, v01.y, a[jj & 1][1]);
-            a[jj & 1][2] = fma(t, v2, a[jj & 1][2]);
+    for (int kt = KT0; kt < 4; ++kt) {
+        const double b = rhs_lane[4 * kt];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][0], acc[mt][1], at[(mt * 4 + kt) * 32 + lane], b);
+    }
+}
+// C fragment -> [3][M] stack in global memory: lane (rho, cp) holds reduced row 8 mt + rho, components 2cp, 2cp+1
+__device__ __forceinline__ void store_stage(double* out, int M, int rho, int cp, const double (&acc)[2][2]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int i = 8 * mt + rho;
+        if (i < M) {
+            if (cp == 0) { out[i] = acc[mt][0]; out[M + i] = acc[mt][1]; }
+            else if (cp == 1) out[2 * M + i] = acc[mt][0];
         }
     }
-    o0 = a[0][0] + a[1][0]; o1 = a[0][1] + a[1][1]; o2 = a[0][2] + a[1][2];
-    o0 += __shfl_xor_sync(0xffffffffu, o0, 16);
-    o1 += __shfl_xor_sync(0xffffffffu, o1, 16);
-    o2 += __shfl_xor_sync(0xffffffffu, o2, 16);
 }
 
 template <int MS>
@@ -100,19 +110,16 @@ __global__ void __maxnreg__(SRI_DMMA_MAXNREG) fused16_dmma_kernel(const FusedPar
 __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma_kernel(const FusedParams p) {
 #endif
     extern __shared__ __align__(16) double smem[];
-    double* tab = smem;                        // OpsLayout16::total doubles (Sp, STt, g, gT, DTI used here)
-    double* stx = smem + OpsLayout16::total;   // 256 doubles
+    double* stx = smem;             // 256 doubles
+    double* tabAS = smem + 256;     // 256
+    double* tabAT = smem + 512;     // 256
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* scr = stx + 256 + warp * DmmaScratch::total;
+    double* scr = smem + kDmmaTabDoubles + warp * DmmaScratch::total;
     double* qnode = scr + DmmaScratch::qnode;
-    double* vec = scr + DmmaScratch::vec;
-    double* vec2 = scr + DmmaScratch::vec2;
-    double* misc = scr + DmmaScratch::misc;
 
     constexpr int kWarps = kDmmaThreads / 32;
     if ((long long)blockIdx.x * kWarps >= p.batch) return;  // whole CTA idle
-    for (int i = threadIdx.x; i < OpsLayout16::total; i += kDmmaThreads) tab[i] = p.ops[i];
-    for (int i = threadIdx.x; i < 256; i += kDmmaThreads) stx[i] = p.ops[DmmaTables::Stx + i];
+    for (int i = threadIdx.x; i < kDmmaTabDoubles; i += kDmmaThreads) smem[i] = p.ops[DmmaTables::Stx + i];
     for (int i = lane; i < DmmaScratch::total; i += 32) scr[i] = 0.0;
     __syncthreads();
 
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
     // fragment coordinates of this lane
     const int rho = lane >> 2, cp = lane & 3;  // C fragment: row rho, columns 2cp, 2cp+1
     const int hi = rho >> 2, rr = rho & 3;     // quaternion row within the tile, component
-    // stage coordinates
+    // node coordinates of the pointwise stage work
     const int row = lane & 15, half = lane >> 4;
 
     // lane constants of the elimination (see tools/dmma_gj_emulator.py)
@@ -134,13 +141,15 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
     const double dpiv0 = (hi == 0 && rr == cp) ? 1.0 : 0.0;
     const double dpiv1 = (hi == 1 && rr == cp) ? 1.0 : 0.0;
     const unsigned hi_mask = hi ? 0x7fffffffu : 0u;
-    // normalisation operand: B[q = cp][n = rho]; even n = 2 s' carries -Rmat(c^-1)[s'][q] = -sg(s',q) conj(c)[s'^q] / |c|^2
+    // normalisation operand: B[q = cp][n = rho]; even n = 2 s' carries Rmat(conj c)[s'][q] = sg(s',q) conj(c)[s'^q]
+    // (odd columns feed C-fragment register 1, which is discarded: don't-care)
     const int sp = rho >> 1;
     const int idxN = sp ^ cp;
-    // sign of -(sg(s',q) conj): negative iff sg and conj have the same sign
-    const unsigned sgN_mask = ((((neg_tab >> (4 * sp + cp)) & 1u) != 0) == (idxN != 0)) ? 0x80000000u : 0u;
+    const unsigned sgN_mask = ((((neg_tab >> (4 * sp + cp)) & 1u) != 0) != (idxN != 0)) ? 0x80000000u : 0u;
     // identity entries of the assembly: tile (t, ct), register e holds delta_ij iff rr == 0, hi == e, cp == t - 4 ct
     const int diag_code = (rr == 0) ? (4 * hi + cp) : -1;
+    // B-fragment read offset into a [4][20] right-hand side
+    const int offb = (rho < 3 ? rho : 3) * 20 + cp;
 
     const long long stride = (long long)gridDim.x * kWarps;
     const long long rod0 = (long long)blockIdx.x * kWarps + warp;
@@ -165,18 +174,19 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
     int it = 0;
     for (long long rod = rod0; rod < p.batch; rod += stride, ++it) {
         const int cur = it & 1;
-        // ---- prefetch: this rod's late inputs and the next rod's strain samples --------------------------------
+        // ---- prefetch: this rod's late inputs (nodal loads shifted to reduced rows, boundary values into k slot 15)
+        //      and the next rod's strain samples -------------------------------------------------------------------
         if (row < N) {
             const int c0 = half ? 2 : 0, c1 = half ? 3 : 2;  // half 0: components 0, 1; half 1: component 2
             for (int c = c0; c < c1; ++c) {
-                if (p.fbar) cp_async8(scr + DmmaScratch::fbar + 16 * c + row, p.fbar + (rod * 3 + c) * N + row);
-                if (p.lbar) cp_async8(scr + DmmaScratch::lbar + 16 * c + row, p.lbar + (rod * 3 + c) * N + row);
+                if (p.fbar && row >= 1) cp_async8(scr + DmmaScratch::fbs + 20 * c + row - 1, p.fbar + (rod * 3 + c) * N + row);
+                if (p.lbar && row >= 1) cp_async8(scr + DmmaScratch::lbs + 16 * c + row - 1, p.lbar + (rod * 3 + c) * N + row);
                 if (p.Gamma) cp_async8(scr + DmmaScratch::gam + 16 * c + row, p.Gamma + (rod * 3 + c) * N + row);
             }
         }
-        if (lane < 3) { if (p.F_tip) cp_async8(misc + lane, p.F_tip + rod * 3 + lane); }
-        else if (lane >= 4 && lane < 7) { if (p.M_tip) cp_async8(misc + lane, p.M_tip + rod * 3 + lane - 4); }
-        else if (lane >= 8 && lane < 11) { if (p.r0) cp_async8(misc + lane, p.r0 + rod * 3 + lane - 8); }
+        if (lane < 3) { if (p.F_tip) cp_async8(scr + DmmaScratch::fbs + 20 * lane + 15, p.F_tip + rod * 3 + lane); }
+        else if (lane >= 4 && lane < 7) { if (p.M_tip) cp_async8(scr + DmmaScratch::xs + 20 * (lane - 4) + 15, p.M_tip + rod * 3 + lane - 4); }
+        else if (lane >= 8 && lane < 11) { if (p.r0) cp_async8(scr + DmmaScratch::bs + 20 * (lane - 8) + 15, p.r0 + rod * 3 + lane - 8); }
         if (rod + stride < p.batch) prefetch_K(rod + stride, cur ^ 1);
         cp_async_commit();
         cp_async_wait<1>();  // everything but the group just committed: this rod's K and q0 have landed
@@ -208,9 +218,11 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
         }
         // ---- Gauss-Jordan over the quaternions on DMMA, static pivot order, software pipelined -----------------
         // Iteration k issues the rank-4 update of step k and, behind it, everything step k+1 needs: its tile row is
-        // updated first, then the next pivot row / pivot element are gathered and the reciprocal chain (the only serial
-        // scalar FP64 work) runs while the other 14 DMMAs of step k go through the pipe; each la[t] is re-gathered
-        // for step k+1 as soon as tile row t has been updated.  k = -1 is the prologue (no update).
+        // updated first, then the next pivot row is gathered and normalised; each la[t] is re-gathered for step k+1 as
+        // soon as tile row t has been updated.  k = -1 is the prologue (no update).
+        // Scalar FP64 instructions share the pipe with the DMMAs and queue behind them, so the serial scalar chain is
+        // kept to three operations per step: U (x) conj(c_kk) is itself a DMMA, whose (column k, w) entry is |c_kk|^2,
+        // and its reciprocal (MUFU seed, e = 1 - nu r0, t2 = e + e^2) is folded into the scaling of that product.
         bool bad = false;
         const int growth_log = p.growth_log;
         double la[8], un[2];
@@ -226,27 +238,27 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                 for (int ct = 0; ct < 2; ++ct)
                     if (8 * ct + 7 > k) dmma(c[nt][ct][0], c[nt][ct][1], la[nt], un[ct]);
             }
-            double un0[2] = {0.0, 0.0}, r0 = 0.0, t2 = 0.0;
+            double un0[2] = {0.0, 0.0}, r0n = 0.0, t2 = 0.0;
             unsigned mx = 0u;
             int thr = 0;
             if (prep) {
                 // next pivot row -> B fragments: lane wants U[s = cp][col = 8 ct + rho]
                 const int srcU = 16 * nh + srcU_base;
-                // this lane's entry of -Rmat(conj c_kk) (operand of the normalisation; odd columns are don't-care)
+                // this lane's entry of Rmat(conj c_kk), straight from the pivot's tile
                 const double pcs = __shfl_sync(0xffffffffu, c[nt][nc][ne], 16 * nh + 4 * idxN + ncp);
                 const double bn0 = flip_sign(pcs, sgN_mask);
 #pragma unroll
                 for (int ct = nc; ct < 2; ++ct) {
                     const double v0 = __shfl_sync(0xffffffffu, c[nt][ct][0], srcU);
                     const double v1 = __shfl_sync(0xffffffffu, c[nt][ct][1], srcU);
-                    un0[ct] = dmma_zero(odd_col ? v1 : v0, bn0);  // -U (x) conj(c_kk), B-fragment layout
+                    un0[ct] = dmma_zero(odd_col ? v1 : v0, bn0);  // U (x) conj(c_kk), B-fragment layout
                 }
-                // its (column k, w) entry is -|c_kk|^2: one shuffle instead of a scalar FP64 reduction, so that the
-                // serial chain on the (shared, DMMA-loaded) FP64 pipe is DMMA -> e -> t2 -> scale
-                const double nu = -__shfl_sync(0xffffffffu, un0[nc], 4 * (kn & 7));
+                const double nu = __shfl_sync(0xffffffffu, un0[nc], 4 * (kn & 7));  // |c_kk|^2
+                double r0;
                 asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(nu));
                 const double e = fma(-nu, r0, 1.0);
                 t2 = fma(e, e, e);  // 1/nu = r0 (1 + e + e^2) to ~1e-16
+                r0n = flip_sign(r0, 0x80000000u);
                 // growth bound in the log domain (hi word of a positive double ~ 2^20 (log2 + 1023)):
                 //   |c_ik| <= G |c_kk|  <=>  2 H(|c_ik|) <= H(nu) + (1023 << 20) + 2^20 log2(G^2)
                 const int hn = __double2hiint(nu);
@@ -272,12 +284,12 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                     if (tt == 0) la[t] -= nh ? dpiv1 : dpiv0;  // pivot row: Rmat(c_kk - 1) leaves the normalised row
                 }
             }
-            // 3. normalise the next pivot row (negated)
+            // 3. -U' = -(U (x) conj c_kk) / nu for the next step
             if (prep) {
                 bad = bad || ((int)mx > thr);
 #pragma unroll
                 for (int ct = 0; ct < 2; ++ct)
-                    if (8 * ct + 7 > kn) { const double a = un0[ct] * r0; un[ct] = fma(a, t2, a); }
+                    if (8 * ct + 7 > kn) { const double a = un0[ct] * r0n; un[ct] = fma(a, t2, a); }
             }
         }
         const bool flagged = __any_sync(0xffffffffu, bad);
@@ -304,7 +316,9 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
         }
 
         if (p.r || p.n || p.m) {
-            // ---- stage 2: r = S (R(q) Gamma) + g r0 ----------------------------------------------------------
+            // ---- stages 2-4 as [16 x 16] x [16 x 3] DMMA contractions against the cached operators; the boundary terms
+            //      (g r0, gT F_tip, gT M_tip) ride along as k index 15, so the only scalar FP64 work left is pointwise:
+            //      R(q) Gamma and the cross product r' x n.
             double bv0 = 0.0, bv1 = 0.0, bv2 = 0.0;
             if (row <= M) {
                 if (p.Gamma) {
@@ -314,65 +328,47 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                     q_rotate_e1(q, bv0, bv1, bv2);
                 }
             }
-            if (half == 0) { quat t; t.w = bv0; t.x = bv1; t.y = bv2; t.z = 0.0; st_quat(vec + 4 * row, t); }
-            // ---- stage 3 right-hand side --------------------------------------------------------------------
-            double F0 = 0.0, F1 = 0.0, F2 = 0.0;
-            if ((p.n || p.m) && p.F_tip) { F0 = misc[0]; F1 = misc[1]; F2 = misc[2]; }
-            const bool contract3 = (p.n || p.m) && p.fbar;
-            if (contract3 && half == 1) {
-                const double dti = tab[OpsLayout16::DTI + row];
-                double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-                if (row < M) { const double* s = scr + DmmaScratch::fbar + row + 1; f0 = s[0]; f1 = s[16]; f2 = s[32]; }
-                quat t; t.w = -f0 - dti * F0; t.x = -f1 - dti * F1; t.y = -f2 - dti * F2; t.z = 0.0;
-                st_quat(vec2 + 4 * row, t);
+            if (half == 0) {
+                double* rp = scr + DmmaScratch::rps + row;
+                rp[0] = bv0; rp[16] = bv1; rp[32] = bv2;
+                if (row < 15) { double* b = scr + DmmaScratch::bs + row; b[0] = bv0; b[20] = bv1; b[40] = bv2; }
             }
             __syncwarp();
+            double acc[2][2];
             if (p.r) {
-                double a0, a1, a2;
-                contract_halves(tab + OpsLayout16::Sp, vec, row, half, a0, a1, a2);
-                if (p.r0) {
-                    const double gi = tab[OpsLayout16::g + row];
-                    a0 = fma(gi, misc[8], a0); a1 = fma(gi, misc[9], a1); a2 = fma(gi, misc[10], a2);
-                }
-                if (keep && row < M) {
-                    double* d = p.r + rod * 3 * M + row;
-                    if (half == 0) { d[0] = a0; d[M] = a1; } else d[2 * M] = a2;
-                }
+                // stage 2: r = Dn_NN^-1 (R(q) Gamma) + g r0^T
+                stage_dmma16<0>(tabAS, scr + DmmaScratch::bs + offb, lane, acc);
+                if (keep) store_stage(p.r + rod * 3 * M, M, rho, cp, acc);
             }
             if (p.n || p.m) {
-                // ---- stage 3: n = D_TT^-1 (-fbar - D_TI F_tip^T); lane `row` = reduced index (node row+1) --------
-                double n0, n1, n2;
-                if (contract3) {
-                    contract_halves(tab + OpsLayout16::STt, vec2, row, half, n0, n1, n2);
-                } else {
-                    const double gi = tab[OpsLayout16::gT + row];
-                    n0 = gi * F0; n1 = gi * F1; n2 = gi * F2;
-                }
-                if (p.n && keep && row < M) {
-                    double* d = p.n + rod * 3 * M + row;
-                    if (half == 0) { d[0] = n0; d[M] = n1; } else d[2 * M] = n2;
-                }
+                // stage 3: n = (-D_TT^-1) fbar[1:] + gT F_tip^T
+                if (p.fbar) stage_dmma16<0>(tabAT, scr + DmmaScratch::fbs + offb, lane, acc);
+                else stage_dmma16<3>(tabAT, scr + DmmaScratch::fbs + offb, lane, acc);
+                if (p.n && keep) store_stage(p.n + rod * 3 * M, M, rho, cp, acc);
                 if (p.m) {
-                    // ---- stage 4: m = D_TT^-1 (-(r' x n + lbar) - D_TI M_tip^T) ------------------------------
-                    const double T0 = misc[4], T1 = misc[5], T2 = misc[6];
-                    const int nb = (row < M) ? row + 1 : row;  // node of this reduced row
-                    const double2 rp01 = *reinterpret_cast<const double2*>(vec + 4 * nb);
-                    const double rp2 = vec[4 * nb + 2];
-                    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-                    if (p.lbar && row < M) { const double* s = scr + DmmaScratch::lbar + row + 1; l0 = s[0]; l1 = s[16]; l2 = s[32]; }
-                    const double dti = tab[OpsLayout16::DTI + row];
-                    const double x0 = rp01.y * n2 - rp2 * n1, x1 = rp2 * n0 - rp01.x * n2, x2 = rp01.x * n1 - rp01.y * n0;
-                    quat t; t.w = -(x0 + l0) - dti * T0; t.x = -(x1 + l1) - dti * T1; t.y = -(x2 + l2) - dti * T2; t.z = 0.0;
-                    if (row >= M) { t.w = 0.0; t.x = 0.0; t.y = 0.0; }
-                    __syncwarp();  // every lane has read vec2 (stage 3) before it is overwritten
-                    if (half == 0) st_quat(vec2 + 4 * row, t);
-                    __syncwarp();
-                    double m0, m1, m2;
-                    contract_halves(tab + OpsLayout16::STt, vec2, row, half, m0, m1, m2);
-                    if (keep && row < M) {
-                        double* d = p.m + rod * 3 * M + row;
-                        if (half == 0) { d[0] = m0; d[M] = m1; } else d[2 * M] = m2;
+                    // stage 4: m = (-D_TT^-1) (r' x n + lbar)[1:] + gT M_tip^T
+                    double* nsv = scr + DmmaScratch::ns;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const int i = 8 * mt + rho;
+                        if (cp == 0) { nsv[i] = acc[mt][0]; nsv[16 + i] = acc[mt][1]; }
+                        else if (cp == 1) nsv[32 + i] = acc[mt][0];
                     }
+                    __syncwarp();
+                    if (half == 0 && row < 15) {
+                        const double n0 = nsv[row], n1 = nsv[16 + row], n2 = nsv[32 + row];
+                        const double* rp = scr + DmmaScratch::rps + row + 1;  // node of reduced row `row`
+                        const double rp0 = rp[0], rp1 = rp[16], rp2 = rp[32];
+                        double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+                        if (p.lbar) { const double* lb = scr + DmmaScratch::lbs + row; l0 = lb[0]; l1 = lb[16]; l2 = lb[32]; }
+                        double* x = scr + DmmaScratch::xs + row;
+                        x[0] = fma(rp1, n2, fma(-rp2, n1, l0));
+                        x[20] = fma(rp2, n0, fma(-rp0, n2, l1));
+                        x[40] = fma(rp0, n1, fma(-rp1, n0, l2));
+                    }
+                    __syncwarp();
+                    stage_dmma16<0>(tabAT, scr + DmmaScratch::xs + offb, lane, acc);
+                    if (keep) store_stage(p.m + rod * 3 * M, M, rho, cp, acc);
                 }
             }
         }
