@@ -30,6 +30,7 @@ SEED = 0x5EED
 METRIC = "rod-integrations/sec (N=16, 4 stages, FP64)"
 # SURVEY 8(d) / BASELINE.md section 2: algorithmic work of one rod-integration, dense real formulation
 FLOPS_PER_ROD_DENSE = 155_700
+DMMA_PER_ROD = 223  # tensor-core instructions the fused kernel issues per rod (csrc/sri_fused16_dmma.cuh)
 BYTES_PER_ROD = 1_992 + 3 * N_NODES * 8  # compulsory HBM traffic incl. the nodal fbar this workload supplies
 
 
@@ -235,7 +236,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         step()
     barrier()
 
-    fp64_peak = h.measure_fp64_peak()  # live roofline denominator (MEASURED_PEAKS.json has no FP64 entry)
+    # live roofline denominators (MEASURED_PEAKS.json has no FP64 entry): scalar DFMA stream and DMMA m8n8k4 stream
+    fp64_peak = h.measure_fp64_peak()
+    dmma_peak = h.measure_dmma_peak()
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -289,7 +292,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         assert torch.equal(hQ[:1000], Q[:1000].cpu()), "host-buffer path and device-buffer path disagree"
         e2e = {"value": world * Be * he / dt, "unit": "rods/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": he, "ms_per_step": dt / he * 1e3,
-               "path": "sri_integrate_all() with pinned host buffers; per step: H2D of K,F_tip,M_tip,fbar, fused kernel, D2H of Q,r,n,m"}
+               "path": "sri_integrate_all() with pinned host buffers; per step: H2D of K,F_tip,M_tip,fbar, fused kernels, D2H of Q,r,n,m"}
         barrier()
 
     # ---- BASELINE configs[1] (10^4 rods on one GPU) timed beside the headline workload, device-resident ----------
@@ -325,17 +328,26 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         traffic = traffic * B if traffic is not None else None
     except Exception:
         pass
-    kernel_ms = ms_step  # one kernel launch per step: the step IS the kernel (events bracket the launches)
+    # Two launches per step: fused16_dmma_kernel (all the work) and the row-pivoting second pass, whose CTAs exit at
+    # once when no rod was handed back (always, on this workload); the events bracket both, so the step time is an
+    # upper bound of the dominant kernel's duration (profiles/*launches.csv: the second pass is ~3 us).
+    kernel_ms = ms_step
     tflops_dense = FLOPS_PER_ROD_DENSE * B / (kernel_ms * 1e-3) * 1e-12
+    peak = max(fp64_peak, dmma_peak)
+    executed = DMMA_PER_ROD * 512 * B / (kernel_ms * 1e-3) * 1e-12
     roofline = {
-        "bound": "fp64", "kernel": "sri::fused16_kernel<15,true>",
-        "achieved": tflops_dense, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops_dense / fp64_peak,
-        "peak_source": "measured live: sri_measure_fp64_peak (register-resident DFMA stream, this GPU, this run); "
-                       "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2",
+        "bound": "tensor", "kernel": "sri::fused16_dmma_kernel<15>",
+        "achieved": tflops_dense, "peak": peak, "unit": "TFLOP/s", "frac": tflops_dense / peak,
+        "peak_source": "FP64 tensor-core (DMMA m8n8k4) stream measured live on this GPU in this run "
+                       f"(sri_measure_dmma_peak: {dmma_peak:.1f}; scalar DFMA stream sri_measure_fp64_peak: {fp64_peak:.1f}); "
+                       "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2; MEASURED_PEAKS.json holds no FP64 figure",
         "flops_per_rod": FLOPS_PER_ROD_DENSE,
         "flops_note": "algorithmic count of SURVEY 8(d) (dense real 60x60 LU + 3 contractions); the kernel solves the "
-                      "same system as a 15x15 quaternion system and executes ~4x fewer flops, so frac may exceed 1; "
-                      "see DESIGN.md for the executed-flop fraction",
+                      "same system as a 15x15 quaternion system, which needs ~4x fewer flops, so frac may exceed 1; "
+                      "`executed` is what the tensor pipe actually does",
+        "executed": {"dmma_per_rod": DMMA_PER_ROD, "tflops": executed, "frac": executed / peak,
+                     "note": "223 DMMA m8n8k4 (512 flop each) per rod: 176 rank-4 updates, 23 pivot-row normalisations, "
+                             "24 stage contractions; dead columns and padding included"},
         "traffic": traffic,
         "hbm": {"achieved": BYTES_PER_ROD * B / (kernel_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": BYTES_PER_ROD * B / (kernel_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src,

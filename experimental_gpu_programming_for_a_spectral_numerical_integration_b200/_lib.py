@@ -66,6 +66,7 @@ SYMBOLS = {
     "sri_kernel_launch_count": (c_int64, []),
     "sri_get_handback_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "sri_measure_fp64_peak": (c_int, [c_void_p, POINTER(c_double)]),
+    "sri_measure_dmma_peak": (c_int, [c_void_p, POINTER(c_double)]),
 }
 
 _lib = None

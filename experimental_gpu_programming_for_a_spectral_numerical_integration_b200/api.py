@@ -282,6 +282,11 @@ class SpectralRodIntegrator:
         _lib.check(self._lib.sri_measure_fp64_peak(self._h, ctypes.byref(v)), "sri_measure_fp64_peak")
         return v.value
 
+    def measure_dmma_peak(self) -> float:
+        v = ctypes.c_double()
+        _lib.check(self._lib.sri_measure_dmma_peak(self._h, ctypes.byref(v)), "sri_measure_dmma_peak")
+        return v.value
+
 
 def kernel_launch_count() -> int:
     return int(_lib.load().sri_kernel_launch_count())

@@ -326,6 +326,22 @@ __global__ void fp64_peak_kernel(double* out, int iters, double s) {
     if (r == 123.456) out[0] = r;
 }
 
+// FP64 tensor-core (DMMA m8n8k4) peak probe: 16 independent accumulator tiles per warp.
+__global__ void dmma_peak_kernel(double* out, int iters, double s) {
+    double c0[16], c1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c0[i] = threadIdx.x * 1e-9 + i; c1[i] = i; }
+    const double a = s, b = 1.0 - s;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sri::dmma_m8n8k4(c0[i], c1[i], a, b);
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r += c0[i] + c1[i];
+    if (r == 123.456) out[0] = r;
+}
+
 // ---- launch helpers --------------------------------------------------------------------------------------------
 
 constexpr int kFusedThreads = SRI_THREADS;
@@ -922,19 +938,18 @@ int sri_get_handback_count(sri_handle h, int64_t* count) {
     return SRI_OK;
 }
 
-int sri_measure_fp64_peak(sri_handle h, double* tflops) {
-    SRI_TRY(check_handle(h));
-    if (!tflops) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_measure_fp64_peak: null argument");
+static int measure_peak(sri_handle h, bool tensor, double* tflops) {
     double* d = nullptr;
     SRI_CUDA(cudaMalloc(&d, 8));
-    const int iters = 8192, threads = 512, blocks = h->sm_count * 2;
+    const int iters = tensor ? 2048 : 8192, threads = 512, blocks = h->sm_count * 2;
     cudaEvent_t e0, e1;
     SRI_CUDA(cudaEventCreate(&e0));
     SRI_CUDA(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
         SRI_CUDA(cudaEventRecord(e0, h->stream));
-        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters, 0.5);
+        if (tensor) dmma_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters, 0.5);
+        else fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters, 0.5);
         g_launches.fetch_add(1);
         SRI_CUDA(cudaEventRecord(e1, h->stream));
         SRI_CUDA(cudaEventSynchronize(e1));
@@ -945,8 +960,21 @@ int sri_measure_fp64_peak(sri_handle h, double* tflops) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d);
-    *tflops = 2.0 * 16 * iters * (double)blocks * threads / (best * 1e-3) * 1e-12;
+    // per thread and iteration: 16 FMA (scalar) or 16 DMMA x 256 FMA / 32 lanes = 128 FMA (tensor)
+    *tflops = 2.0 * (tensor ? 128.0 : 16.0) * iters * (double)blocks * threads / (best * 1e-3) * 1e-12;
     return SRI_OK;
+}
+
+int sri_measure_fp64_peak(sri_handle h, double* tflops) {
+    SRI_TRY(check_handle(h));
+    if (!tflops) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_measure_fp64_peak: null argument");
+    return measure_peak(h, false, tflops);
+}
+
+int sri_measure_dmma_peak(sri_handle h, double* tflops) {
+    SRI_TRY(check_handle(h));
+    if (!tflops) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_measure_dmma_peak: null argument");
+    return measure_peak(h, true, tflops);
 }
 
 }  // extern "C"

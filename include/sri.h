@@ -166,6 +166,9 @@ int64_t sri_kernel_launch_count(void);
 int sri_get_handback_count(sri_handle h, int64_t* count);
 /* Runs the library's FP64 FMA peak probe on the handle's device and returns TFLOP/s (roofline denominator). */
 int sri_measure_fp64_peak(sri_handle h, double* tflops);
+/* The same for the FP64 tensor cores (stream of independent DMMA m8n8k4): the roofline denominator of the N <= 16
+ * fused kernel, whose elimination and stage contractions run there. */
+int sri_measure_dmma_peak(sri_handle h, double* tflops);
 
 #ifdef __cplusplus
 }
