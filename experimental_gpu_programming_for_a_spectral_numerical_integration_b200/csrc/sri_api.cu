@@ -17,6 +17,7 @@
 #include "sri_generic.cuh"
 #include "sri_stage_dmma.cuh"
 #include "sri_tiled.cuh"
+#include "sri_tiled_dmma.cuh"
 #include "sri_host_math.hpp"
 
 namespace {
@@ -48,6 +49,7 @@ struct sri_context {
     int R = 0;                   // generic kernel: row lanes (32 or 64); 0 for the N <= 16 kernel
     size_t generic_smem = 0;
     int generic_blocks_per_sm = 0;
+    double* d_ops2 = nullptr;    // N > 16: tables of the DMMA kernel (Stx | AS | AT, TiledDmmaCfg)
     double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
@@ -347,8 +349,37 @@ __global__ void dmma_peak_kernel(double* out, int iters, double s) {
 constexpr int kFusedThreads = SRI_THREADS;
 constexpr size_t kFusedSmem = (sri::OpsLayout16::total + (kFusedThreads / 32) * sri::kWarpScratch16) * sizeof(double);
 
+int list_reserve(sri_context* h, int slot, long long batch);
+
 template <bool SOLVE>
-int launch_generic(sri_context* h, const sri::FusedParams& p, cudaStream_t stream) {
+int launch_generic(sri_context* h, const sri::FusedParams& p_in, cudaStream_t stream, int list_slot = 3) {
+    sri::FusedParams p = p_in;
+    if (SOLVE && h->use_dmma) {
+        // first pass: static-order elimination on the FP64 tensor cores, one rod per CTA
+        if (p.batch > 0x7fffffffLL) return fail(SRI_ERR_INVALID_ARGUMENT, "batch too large for one call (2^31 rods)");
+        SRI_TRY(list_reserve(h, list_slot, p.batch));
+        {
+            const double g2 = h->dmma_growth * h->dmma_growth;
+            const double lg = (g2 > 0.0) ? std::log2(g2) * 1048576.0 : -2.0e9;
+            p.growth_log = (int)std::lround(std::max(-2.0e9, std::min(2.0e9, lg)));
+        }
+        p.ops2 = h->d_ops2;
+        p.rod_count = h->d_list[list_slot];
+        p.rod_list = h->d_list[list_slot] + 4;
+        SRI_CUDA(cudaMemsetAsync(p.rod_count, 0, sizeof(int), stream));
+        const long long dcap = (long long)h->sm_count * h->dmma_blocks_per_sm;
+        const int dgrid = (int)(p.batch < dcap ? p.batch : dcap);
+        if (h->R == 32) {
+            using Cfg = sri::TiledDmmaCfg<4, 4, 4>;
+            sri::tiled_dmma_kernel<4, 4, 4><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
+        } else {
+            using Cfg = sri::TiledDmmaCfg<2, 8, 16>;
+            sri::tiled_dmma_kernel<2, 8, 16><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
+        }
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+        // second pass (row pivoting) over the rods handed back; CTAs without work exit at once
+    }
     const long long cap = (long long)h->sm_count * h->generic_blocks_per_sm;
     const long long groups = (h->R == 32) ? (p.batch + 1) / 2 : p.batch;  // rods per CTA iteration: 2 (N <= 32) or 1
     const int grid = (int)(groups < cap ? groups : cap);
@@ -380,7 +411,7 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
     if (p_in.batch <= 0) return SRI_OK;
     sri::FusedParams p = p_in;
     if (use_handle_stream) stream = h->stream;
-    if (h->R != 0) return launch_generic<SOLVE>(h, p, stream);
+    if (h->R != 0) return launch_generic<SOLVE>(h, p, stream, list_slot);
     const long long pairs = (p.batch + 1) / 2;
     const long long want = (pairs + (kFusedThreads / 32) - 1) / (kFusedThreads / 32);
     const int per_sm = SOLVE ? h->fused_blocks_per_sm : h->stage_blocks_per_sm;
@@ -630,6 +661,38 @@ int sri_create(int N, int device, sri_handle* out) {
         }
         SRI_CUDA(cudaMalloc(&h->d_ops16, sizeof(double) * L.total()));
         SRI_CUDA(cudaMemcpy(h->d_ops16, t.data(), sizeof(double) * L.total(), cudaMemcpyHostToDevice));
+        {
+            // tables of the DMMA kernel: Stx [QR][NC] | AS | AT (A fragments of the stage operators, last k index =
+            // boundary term), QR = NC = R
+            const int R = h->R, KT = R / 4;
+            std::vector<double> t2((size_t)3 * R * R, 0.0);
+            for (int i = 0; i < M; ++i) {
+                for (int j = 0; j < M; ++j) t2[(size_t)i * R + j] = -0.5 * h->ops.S[j * M + i];
+                t2[(size_t)i * R + R - 1] = h->ops.g[i];
+            }
+            for (int mt = 0; mt < R / 8; ++mt)
+                for (int kt = 0; kt < KT; ++kt)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int i = 8 * mt + lane / 4, j = 4 * kt + lane % 4;
+                        double sv = 0.0, tv = 0.0;
+                        if (i < M && j < M) { sv = h->ops.S[j * M + i]; tv = -h->ops.ST[j * M + i]; }
+                        if (i < M && j == R - 1) { sv = h->ops.g[i]; tv = h->ops.gT[i]; }
+                        t2[(size_t)R * R + (size_t)(mt * KT + kt) * 32 + lane] = sv;
+                        t2[(size_t)2 * R * R + (size_t)(mt * KT + kt) * 32 + lane] = tv;
+                    }
+            SRI_CUDA(cudaMalloc(&h->d_ops2, sizeof(double) * t2.size()));
+            SRI_CUDA(cudaMemcpy(h->d_ops2, t2.data(), sizeof(double) * t2.size(), cudaMemcpyHostToDevice));
+            if (R == 32) {
+                using Cfg = sri::TiledDmmaCfg<4, 4, 4>;
+                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+                SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<4, 4, 4>, Cfg::threads, Cfg::smem_bytes));
+            } else {
+                using Cfg = sri::TiledDmmaCfg<2, 8, 16>;
+                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+                SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<2, 8, 16>, Cfg::threads, Cfg::smem_bytes));
+            }
+            if (h->dmma_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
+        }
         if (h->R == 32) {
             h->generic_smem = sri::TiledSmem<16, 4>::total() * sizeof(double);
             SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
@@ -672,6 +735,8 @@ int sri_create(int N, int device, sri_handle* out) {
         if (h->dmma_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
         // Both are sm_100a kernels of this library; SRI_FUSED16_IMPL=scalar selects the row-pivoting scalar kernel for
         // every rod (A/B measurements), the default is the DMMA elimination with the scalar kernel as its second pass.
+    }
+    {
         const char* impl = std::getenv("SRI_FUSED16_IMPL");
         h->use_dmma = !(impl && std::strcmp(impl, "scalar") == 0);
         if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
@@ -684,6 +749,7 @@ int sri_destroy(sri_handle h) {
     if (!h) return SRI_OK;
     cudaSetDevice(h->device);
     if (h->d_ops16) cudaFree(h->d_ops16);
+    if (h->d_ops2) cudaFree(h->d_ops2);
     if (h->d_tnodes) cudaFree(h->d_tnodes);
     if (h->d_reduce) cudaFree(h->d_reduce);
     if (h->d_ccw) cudaFree(h->d_ccw);

@@ -47,6 +47,7 @@ struct FusedParams {
     long long batch;
     int N, M;
     const double* ops;  // OpsLayout16 (device)
+    const double* ops2; // N > 16: tables of the DMMA kernel (TiledDmmaCfg: Stx | AS | AT)
     const double* K;
     const double* q0;
     const double* r0;

@@ -66,14 +66,18 @@ __global__ void __launch_bounds__(32 * H, (LPR == 16 ? 3 : 1)) tiled_kernel(cons
     double* Kb_t = smem + SM::Kb() + tsub * 192;
     double* misc_t = smem + SM::misc() + tsub * 16;
 
+    // second pass over the rods the DMMA kernel (sri_tiled_dmma.cuh) handed back: rods rod_list[0 .. *rod_count)
+    const bool listed = SOLVE && p.rod_list != nullptr;
+    const long long batch = listed ? (long long)*p.rod_count : p.batch;
+    const long long groups = (batch + RPW - 1) / RPW;
+    if ((long long)blockIdx.x >= groups) return;  // whole CTA idle (the usual case of a second pass)
     for (int idx = threadIdx.x; idx < L.total(); idx += blockDim.x) tab[idx] = p.ops[idx];
     __syncthreads();
-
-    const long long groups = (p.batch + RPW - 1) / RPW;
     for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
         // ---- inputs (stage-phase mapping: thread tn of rod tsub) --------------------------------------------
-        const long long trod = grp * RPW + tsub;
-        const bool tlive = trod < p.batch;
+        const long long tidx = grp * RPW + tsub;
+        const bool tlive = tidx < batch;
+        const long long trod = (tlive && listed) ? (long long)p.rod_list[tidx] : tidx;
         if (SOLVE && tn < 64) {
             double k0 = 0.0, k1 = 0.0, k2 = 0.0;
             if (tlive && tn < N) { const double* s = p.K + trod * 3 * N + tn; k0 = s[0]; k1 = s[N]; k2 = s[2 * N]; }

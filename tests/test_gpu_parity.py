@@ -155,11 +155,11 @@ def test_large_curvature_needs_pivoting(h16, oracle16, torch_mod):
         assert rel_err(got[s], ref[s]) <= 1e-10, s
 
 
-def _handle_with_env(monkeypatch, **env):
+def _handle_with_env(monkeypatch, N=16, **env):
     from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    h = SpectralRodIntegrator(16, 0)  # the environment is read by sri_create
+    h = SpectralRodIntegrator(N, 0)  # the environment is read by sri_create
     for k in env:
         monkeypatch.delenv(k)
     return h
@@ -222,6 +222,31 @@ def test_large_curvature_static_order_vs_pivoting(monkeypatch, sri_lib, oracle16
     assert (got["info"] == 0).all()
     for s in "Qrnm":
         assert rel_err(got[s], scalar[s]) <= 1e-9, s
+
+
+@pytest.mark.parametrize("N,batch", [(17, 200), (32, 300), (33, 150), (64, 100)])
+def test_high_resolution_dmma_and_handback(monkeypatch, sri_lib, make_oracle, torch_mod, N, batch):
+    """17 <= N <= 64: the multi-warp DMMA elimination takes no second pass on the benchmark strain range; with a zero
+    growth bound every rod is handed back and the result equals the all-scalar (row-pivoting) run bit for bit."""
+    o = make_oracle(N)
+    K, F, Mt, fb = o.generate_rods(0x5EED, 31, batch)
+    ref = o.integrate_all(K, F, Mt, fbar=fb)
+    hd = _handle_with_env(monkeypatch, N)
+    hs = _handle_with_env(monkeypatch, N, SRI_FUSED16_IMPL="scalar")
+    hb = _handle_with_env(monkeypatch, N, SRI_DMMA_GROWTH="0")
+    try:
+        got = _gpu_all(hd, torch_mod, K, F, Mt, fbar=fb)
+        n_default = hd.handback_count()
+        scalar = _gpu_all(hs, torch_mod, K, F, Mt, fbar=fb)
+        back = _gpu_all(hb, torch_mod, K, F, Mt, fbar=fb)
+        n_back = hb.handback_count()
+    finally:
+        hd.close(); hs.close(); hb.close()
+    assert n_default == 0 and n_back == batch
+    assert (got["info"] == 0).all() and (back["info"] == 0).all()
+    for s in "Qrnm":
+        assert rel_err(got[s], ref[s]) <= TOL, (N, s, rel_err(got[s], ref[s]))
+        assert np.array_equal(back[s], scalar[s]), (N, s)
 
 
 def test_shape_residual(h16, oracle16, torch_mod):
