@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(32 * W, (W == 4 ? 4 : 1)) tiled_dmma_kernel(co
         // pivot column of step kn -> A fragments of this warp's tiles (+ growth maximum over the rows below the pivot)
         auto gatherL = [&](auto kcn_c, auto ken_c, int pn) {
             constexpr int KCn = decltype(kcn_c)::value, KEn = decltype(ken_c)::value;
+            constexpr int tlo = (4 * KCn) / W;
             const int Tn = 4 * KCn + pn;  // row tile of the pivot
             const int srcL = srcL_base + pn;
             mx = 0u;
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(32 * W, (W == 4 ? 4 : 1)) tiled_dmma_kernel(co
                 if (T > Tn) mx = max(mx, h);
                 else if (T == Tn && KEn == 0) mx = max(mx, h & hi_mask);
                 la[tl] = flip_sign(v, sgL_mask);
-                if (T == Tn) la[tl] -= KEn ? dpiv1 : dpiv0;  // warp-uniform: pivot row, Rmat(c_kk - 1)
             }
+            if (w == (4 * KCn) % W + pn) la[tlo] -= KEn ? dpiv1 : dpiv0;  // owner warp only: pivot row, Rmat(c_kk - 1)
         };
         auto owner_of = [&](int kc, int pn) { return (4 * kc) % W + pn; };
 
