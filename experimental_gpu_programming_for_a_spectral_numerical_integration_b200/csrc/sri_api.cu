@@ -393,8 +393,10 @@ int launch_generic(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
 }
 
 int list_reserve(sri_context* h, int slot, long long batch) {
-    const size_t need = (size_t)batch + 4;
+    size_t need = (size_t)batch + 4;
     if (h->list_cap[slot] < need) {
+        // grow generously (>= 2^20 entries, then doubling): a reallocation synchronises the device
+        need = std::max(need, std::max((size_t)1 << 20, 2 * h->list_cap[slot]));
         if (h->d_list[slot]) SRI_CUDA(cudaFree(h->d_list[slot]));
         h->d_list[slot] = nullptr;
         h->list_cap[slot] = 0;

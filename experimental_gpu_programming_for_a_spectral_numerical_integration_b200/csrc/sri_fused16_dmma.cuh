@@ -65,8 +65,11 @@ struct DmmaScratch {
 };
 constexpr size_t kDmmaSmem = (kDmmaTabDoubles + (kDmmaThreads / 32) * DmmaScratch::total) * sizeof(double);
 
+#ifndef SRI_DMMA_VOLATILE
+#define SRI_DMMA_VOLATILE
+#endif
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm SRI_DMMA_VOLATILE("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ double dmma_zero(double a, double b) {  // column 0/2/4/6 of A*B (C fragment register 0)
     double d0, d1;
@@ -289,7 +292,13 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
                 bad = bad || ((int)mx > thr);
 #pragma unroll
                 for (int ct = 0; ct < 2; ++ct)
-                    if (8 * ct + 7 > kn) { const double a = un0[ct] * r0n; un[ct] = fma(a, t2, a); }
+                    if (8 * ct + 7 > kn) {
+#ifdef SRI_DMMA_RFOLD
+                        un[ct] = un0[ct] * fma(r0n, t2, r0n);
+#else
+                        const double a = un0[ct] * r0n; un[ct] = fma(a, t2, a);
+#endif
+                    }
             }
         }
         const bool flagged = __any_sync(0xffffffffu, bad);

@@ -36,8 +36,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+// 4 CTAs per SM (<= 128 registers): measured best on B200 -- with fewer registers (5-6 CTAs) the loads of a tile no longer
+// all stay in flight (position -16..-29 %), with the compiler's free choice (96..160 registers) stress is 15 % slower.
+#ifndef SRI_STAGE_MINBLOCKS
+#define SRI_STAGE_MINBLOCKS 4
+#endif
+#define SRI_STAGE_BOUNDS __launch_bounds__(128, SRI_STAGE_MINBLOCKS)
 template <int STAGE>
-__global__ void __launch_bounds__(128) stage_dmma_kernel(const FusedParams p) {
+__global__ void SRI_STAGE_BOUNDS stage_dmma_kernel(const FusedParams p) {
     const int lane = threadIdx.x & 31;
     const int lr = lane >> 2, lk = lane & 3;  // tile-local rod (B/C row group) and k offset
     const int M = p.M, N = p.N;
