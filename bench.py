@@ -193,6 +193,29 @@ class ClockSampler:
 #  GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 
+def _bind_to_gpu_numa_node(torch, local_rank: int):
+    """Multi-rank runs: pin this rank's CPU affinity to the NUMA node of its GPU before the pinned host buffers of the
+    end-to-end leg are allocated (first touch), so that eight ranks do not stream their H2D/D2H traffic across sockets.
+    Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -204,6 +227,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         raise RuntimeError("bench.py --impl b200 needs a CUDA device: the integration path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = _bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     B, N, M = args.rods, N_NODES, N_NODES - 1
     f64 = torch.float64
 
@@ -291,7 +315,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         d2h = (hQ.numel() + hr.numel() + hn.numel() + hm.numel()) * 8
         assert torch.equal(hQ[:1000], Q[:1000].cpu()), "host-buffer path and device-buffer path disagree"
         e2e = {"value": world * Be * he / dt, "unit": "rods/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": he, "ms_per_step": dt / he * 1e3,
+               "steps": he, "ms_per_step": dt / he * 1e3, "rank0_numa_node": numa,
                "path": "sri_integrate_all() with pinned host buffers; per step: H2D of K,F_tip,M_tip,fbar, fused kernels, D2H of Q,r,n,m"}
         barrier()
 

@@ -8,14 +8,16 @@ from .api import (  # noqa: F401
     GetCoefficients_c,
     Phi,
     SpectralRodIntegrator,
+    ad,
     getDn,
     integratePosition,
     integrateQuaternions,
     kernel_launch_count,
+    skew,
 )
 from ._lib import SriError  # noqa: F401
 
 __all__ = [
     "ComputeChebyshevPoints", "GetCoefficients_c", "Phi", "SpectralRodIntegrator", "getDn",
-    "integratePosition", "integrateQuaternions", "kernel_launch_count", "SriError",
+    "integratePosition", "integrateQuaternions", "kernel_launch_count", "SriError", "skew", "ad",
 ]

@@ -88,6 +88,20 @@ def Phi(na: int, ne: int, X: float, begin: float = 0.0, end: float = 1.0) -> np.
 
 # ---- handle -----------------------------------------------------------------------------------------------------
 
+def skew(v) -> np.ndarray:
+    """3x3 hat map, skew(v) w = v x w (include/utilities.h:16-24)."""
+    v = np.asarray(v, dtype=np.float64).reshape(3)
+    return np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def ad(strain) -> np.ndarray:
+    """6x6 se(3) adjoint of the strain twist [k; gamma]: [[k^, 0], [gamma^, k^]] (include/utilities.h:27-37)."""
+    s = np.asarray(strain, dtype=np.float64).reshape(6)
+    out = np.zeros((6, 6))
+    out[:3, :3] = skew(s[:3]); out[3:, :3] = skew(s[3:]); out[3:, 3:] = skew(s[:3])
+    return out
+
+
 class SpectralRodIntegrator:
     """Owns an sri_handle: the cached operator set for N nodes on one CUDA device."""
 
@@ -243,6 +257,19 @@ class SpectralRodIntegrator:
             "sri_shape_residual",
         )
         return rho
+
+    def wrench_local(self, Q, n, m, F_tip, M_tip, q0=None, out=None):
+        """Local-frame wrench [R^T m; R^T n] at all N nodes, [batch][6][N] (rod_modeling.pdf eqs. 1.29, 2.18)."""
+        self._follow_torch(Q)
+        batch = Q.shape[0]
+        if out is None:
+            out = _empty_like_kind(Q, (batch, 6, self.N))
+        _lib.check(
+            self._lib.sri_wrench_local(self._h, batch, _ptr(Q, "Q"), _ptr(q0, "q0"), _ptr(n, "n"), _ptr(m, "m"),
+                                       _ptr(F_tip, "F_tip"), _ptr(M_tip, "M_tip"), _ptr(out, "Lambda")),
+            "sri_wrench_local",
+        )
+        return out
 
     def project_onto_modes(self, f, ne: int, out=None):
         """Nodal field f [batch][3][N] -> modal coordinates [batch][3*ne] (Clenshaw-Curtis Galerkin projection)."""

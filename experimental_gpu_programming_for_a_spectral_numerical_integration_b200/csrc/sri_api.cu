@@ -220,6 +220,39 @@ __global__ void shape_residual_kernel(long long batch, int N, const double* __re
     }
 }
 
+// Lambda[b][0..2][i] = R(q_i)^T m_i, Lambda[b][3..5][i] = R(q_i)^T n_i; one thread per (rod, node)
+__global__ void wrench_local_kernel(long long batch, int N, const double* __restrict__ Q, const double* __restrict__ q0,
+                                    const double* __restrict__ n, const double* __restrict__ m,
+                                    const double* __restrict__ F_tip, const double* __restrict__ M_tip,
+                                    double* __restrict__ Lambda) {
+    const int M = N - 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * N) return;
+    const long long b = idx / N;
+    const int i = (int)(idx % N);
+    sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+    if (i < M) {
+        const double* s = Q + b * 4 * M + i;
+        q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M];
+    } else if (q0) {
+        const double* s = q0 + b * 4;
+        q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3];
+    }
+    double m0, m1, m2, n0, n1, n2;
+    if (i == 0) {
+        const double* s = M_tip + b * 3; m0 = s[0]; m1 = s[1]; m2 = s[2];
+        const double* f = F_tip + b * 3; n0 = f[0]; n1 = f[1]; n2 = f[2];
+    } else {
+        const double* s = m + b * 3 * M + (i - 1); m0 = s[0]; m1 = s[M]; m2 = s[2 * M];
+        const double* f = n + b * 3 * M + (i - 1); n0 = f[0]; n1 = f[M]; n2 = f[2 * M];
+    }
+    double c0, c1, c2, f0, f1, f2;
+    sri::q_rotate_T(q, m0, m1, m2, c0, c1, c2);
+    sri::q_rotate_T(q, n0, n1, n2, f0, f1, f2);
+    double* d = Lambda + b * 6 * N + i;
+    d[0] = c0; d[N] = c1; d[2 * N] = c2; d[3 * N] = f0; d[4 * N] = f1; d[5 * N] = f2;
+}
+
 // out[b][c*ne+k] = sum_i w_i P_k(t_i) f[b][c][i]: one thread per (rod, component), Legendre recurrence per node.
 __global__ void project_onto_modes_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
                                           const double* __restrict__ ccw, const double* __restrict__ f,
@@ -949,6 +982,28 @@ int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const doubl
     }
     const long long total = (long long)batch * N;
     shape_residual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, N, dK, dK0, H[0], H[1], H[2], dQ, dq0, dm, dMt, drho, dred);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* n, const double* m,
+                     const double* F_tip, const double* M_tip, double* Lambda) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || (batch > 0 && (!Q || !n || !m || !F_tip || !M_tip || !Lambda))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_wrench_local: bad arguments");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    Staging st(h);
+    const double *dQ, *dq0, *dn, *dm, *dF, *dMt; double* dL;
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &dq0));
+    SRI_TRY(st.in(n, (size_t)batch * 3 * M, &dn));
+    SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
+    SRI_TRY(st.in(F_tip, (size_t)batch * 3, &dF));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
+    SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &dL));
+    const long long total = (long long)batch * N;
+    wrench_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, N, dQ, dq0, dn, dm, dF, dMt, dL);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();

@@ -136,6 +136,14 @@ int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const doubl
                        const double* Q, const double* q0, const double* m, const double* M_tip, double* rho,
                        double* norm2_and_max);
 
+/* Local-frame wrench Lambda = [C; N] = [R(q)^T m; R(q)^T n] at all N nodes: the state of the local-frame statics
+ * Lambda' = ad^T_xi Lambda - Fbar (rod_modeling.pdf eqs. 1.29, 2.18), couple first as in ad()'s [k; gamma] ordering
+ * (include/utilities.h:27-37).  Evaluated pointwise from the global-frame stages (n = R N, m = R C), not by a second
+ * collocation solve.  Node 0 carries (M_tip, F_tip), node N-1 the base rotation q0 (NULL => identity).
+ * Q [batch][4][M]; n, m [batch][3][M]; F_tip, M_tip [batch][3]; Lambda [batch][6][N]. */
+int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* n, const double* m,
+                     const double* F_tip, const double* M_tip, double* Lambda);
+
 /* Galerkin projection of a nodal field onto the Legendre strain modes (rod_modeling.pdf eqs. 2.14, 2.16; the
  * transpose of Phi, include/utilities.h:49-67): out[b][c*ne+k] = sum_i w_i P_k(2 x_i - 1) f[b][c][i], with w the
  * Clenshaw-Curtis weights of the N Chebyshev nodes on [0,1].  f [batch][3][N] -> out [batch][3*ne]. */

@@ -50,6 +50,23 @@ private:
     std::vector<double> d_;
 };
 
+// skew(v): 3x3 hat map, skew(v) w = v x w                                   (include/utilities.h:16-24)
+inline Matrix skew(const std::array<double, 3>& v) {
+    Matrix m(3, 3);
+    m(0, 1) = -v[2]; m(0, 2) = v[1];
+    m(1, 0) = v[2];  m(1, 2) = -v[0];
+    m(2, 0) = -v[1]; m(2, 1) = v[0];
+    return m;
+}
+// ad(strain): 6x6 se(3) adjoint of the strain twist [k; gamma] = [[k^, 0], [gamma^, k^]]   (include/utilities.h:27-37)
+inline Matrix ad(const std::array<double, 6>& strain) {
+    const Matrix kh = skew({strain[0], strain[1], strain[2]}), gh = skew({strain[3], strain[4], strain[5]});
+    Matrix m(6, 6);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { m(i, j) = kh(i, j); m(3 + i, j) = gh(i, j); m(3 + i, 3 + j) = kh(i, j); }
+    return m;
+}
+
 inline std::ostream& operator<<(std::ostream& os, const Matrix& m) {
     for (int i = 0; i < m.rows(); ++i) {
         if (i) os << "\n";

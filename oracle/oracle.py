@@ -76,6 +76,7 @@ class Oracle:
         L.sri_oracle_integrate_all_batch.restype = c_int
         L.sri_oracle_integrate_all_batch.argtypes = [c_int, c_long] + [c_void_p] * 12 + [c_int, c_int]
         L.sri_oracle_shape_residual.argtypes = [c_void_p] * 9
+        L.sri_oracle_wrench_local.argtypes = [c_void_p] * 8
         L.sri_oracle_max_threads.restype = c_int
         L.sri_oracle_generate_rods.argtypes = [c_int, ctypes.c_uint64, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p]
         self._ops = L.sri_oracle_ops_create(self.N)
@@ -166,6 +167,15 @@ class Oracle:
                 _p(np.ascontiguousarray(Q[b])), None if q0 is None else _p(np.ascontiguousarray(q0[b])),
                 _p(np.ascontiguousarray(m[b])), _p(np.ascontiguousarray(M_tip[b])), rho[b].ctypes.data)
         return rho
+
+    def wrench_local(self, Q, n, m, F_tip, M_tip, q0=None) -> np.ndarray:
+        B = Q.shape[0]
+        lam = np.empty((B, 6, self.N))
+        cz = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        for b in range(B):
+            self.lib.sri_oracle_wrench_local(self._ops, _p(cz(Q[b])), None if q0 is None else _p(cz(q0[b])), _p(cz(n[b])),
+                                             _p(cz(m[b])), _p(cz(F_tip[b])), _p(cz(M_tip[b])), lam[b].ctypes.data)
+        return lam
 
     def generate_rods(self, seed: int, first_rod: int, batch: int):
         K = np.empty((batch, 3, self.N)); F = np.empty((batch, 3)); Mt = np.empty((batch, 3)); fb = np.empty((batch, 3, self.N))

@@ -425,6 +425,31 @@ void sri_oracle_shape_residual(const sri_oracle_ops* o, const double* K, const d
     }
 }
 
+/* Local-frame wrench Lambda = [C; N] = [R^T m; R^T n] at all N nodes (rod_modeling.pdf eqs. 1.29, 2.18: the quantity
+ * that obeys Lambda' = ad^T_xi Lambda - Fbar; couple first, matching the [k; gamma] ordering of ad(), utilities.h:27-37).
+ * Node 0 carries the tip wrench (M_tip, F_tip), node N-1 the base rotation q0.  Lambda is [6][N]. */
+void sri_oracle_wrench_local(const sri_oracle_ops* o, const double* Q, const double* q0, const double* n, const double* m,
+                             const double* F_tip, const double* M_tip, double* Lambda)
+{
+    const int N = o->N, M = o->M;
+    static const double q_default[4] = {1.0, 0.0, 0.0, 0.0};
+    if (!q0) q0 = q_default;
+    double R[9];
+    for (int i = 0; i < N; ++i) {
+        if (i < M) quat_to_rot(Q[i], Q[i + M], Q[i + 2 * M], Q[i + 3 * M], R);
+        else quat_to_rot(q0[0], q0[1], q0[2], q0[3], R);
+        double mi[3], ni[3];
+        for (int c = 0; c < 3; ++c) {
+            mi[c] = (i == 0) ? M_tip[c] : m[c * M + (i - 1)];
+            ni[c] = (i == 0) ? F_tip[c] : n[c * M + (i - 1)];
+        }
+        for (int c = 0; c < 3; ++c) {
+            Lambda[c * N + i] = R[0 * 3 + c] * mi[0] + R[1 * 3 + c] * mi[1] + R[2 * 3 + c] * mi[2];
+            Lambda[(3 + c) * N + i] = R[0 * 3 + c] * ni[0] + R[1 * 3 + c] * ni[1] + R[2 * 3 + c] * ni[2];
+        }
+    }
+}
+
 /* ---- batched driver (OpenMP over rods) ----------------------------------------------------------------- */
 
 /* All four stages for `batch` rods.  Layouts match include/sri.h: K,Gamma,fbar,lbar [batch][3][N];

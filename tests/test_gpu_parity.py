@@ -249,6 +249,26 @@ def test_high_resolution_dmma_and_handback(monkeypatch, sri_lib, make_oracle, to
         assert np.array_equal(back[s], scalar[s]), (N, s)
 
 
+def test_wrench_local_frame(h16, oracle16, torch_mod):
+    """SURVEY 8 f4 (pointwise form): Lambda = [R^T m; R^T n] at all nodes against the oracle; for a straight unloaded-in-
+    couple rod the local force equals the global one."""
+    rng = np.random.default_rng(9)
+    B = 321
+    K, F, Mt, fb = oracle16.generate_rods(99, 0, B)
+    q0 = rng.normal(size=(B, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    ref = oracle16.integrate_all(K, F, Mt, q0=q0, fbar=fb)
+    lam_ref = oracle16.wrench_local(ref["Q"], ref["n"], ref["m"], F, Mt, q0=q0)
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    lam = h16.wrench_local(t(ref["Q"]), t(ref["n"]), t(ref["m"]), t(F), t(Mt), q0=t(q0))
+    h16.synchronize()
+    assert rel_err(lam.cpu().numpy(), lam_ref) <= TOL
+    # host buffers, default q0, K = 0: R = I, so Lambda = [m; n]
+    K0 = np.zeros((4, 3, 16))
+    out = h16.integrate_all(K0, F[:4], Mt[:4])
+    lam0 = h16.wrench_local(out["Q"], out["n"], out["m"], F[:4], Mt[:4])
+    assert np.abs(lam0[:, 3:, 1:] - out["n"]).max() <= 1e-13 and np.abs(lam0[:, :3, 1:] - out["m"]).max() <= 1e-13
+
+
 def test_shape_residual(h16, oracle16, torch_mod):
     B = 400
     K, F, Mt, fb = oracle16.generate_rods(21, 0, B)
