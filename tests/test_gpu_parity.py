@@ -249,6 +249,33 @@ def test_high_resolution_dmma_and_handback(monkeypatch, sri_lib, make_oracle, to
         assert np.array_equal(back[s], scalar[s]), (N, s)
 
 
+@pytest.mark.parametrize("N", [16, 32])
+def test_non_finite_and_singular_inputs_are_reported_not_fatal(sri_lib, make_oracle, torch_mod, N):
+    """A rod with NaN / Inf strain samples must not disturb its neighbours nor hang the kernel: the tensor-core pass
+    flags it (the growth check fails on a non-finite pivot), the row-pivoting pass reports it through info[] or leaves
+    non-finite outputs, as the reference would (main.cpp:113 has no checks).  All other rods stay within tolerance."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    o = make_oracle(N)
+    B = 200
+    K, F, Mt, fb = o.generate_rods(0x5EED, 1234, B)
+    ref = o.integrate_all(K, F, Mt, fbar=fb)
+    Kbad = K.copy()
+    bad = [3, 77, 150]
+    Kbad[3, 1, 2] = np.nan
+    Kbad[77, 0, 0] = np.inf
+    Kbad[150] = 1e200
+    with SpectralRodIntegrator(N, 0) as h:
+        got = _gpu_all(h, torch_mod, Kbad, F, Mt, fbar=fb)
+        nback = h.handback_count()
+    assert 1 <= nback <= len(bad) + 0, nback
+    good = np.setdiff1d(np.arange(B), bad)
+    for s in "Qrnm":
+        assert rel_err(got[s][good], ref[s][good]) <= TOL, s
+    assert (got["info"][good] == 0).all()
+    for b in (3, 77):
+        assert got["info"][b] != 0 or not np.isfinite(got["Q"][b]).all()
+
+
 def test_wrench_local_frame(h16, oracle16, torch_mod):
     """SURVEY 8 f4 (pointwise form): Lambda = [R^T m; R^T n] at all nodes against the oracle; for a straight unloaded-in-
     couple rod the local force equals the global one."""
