@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,6 +17,7 @@
 #include "sri_fused16_dmma.cuh"
 #include "sri_generic.cuh"
 #include "sri_stage_dmma.cuh"
+#include "sri_stage_tma.cuh"
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
 #include "sri_host_math.hpp"
@@ -57,7 +59,9 @@ struct sri_context {
     int stage_blocks_per_sm = 0;
     int dmma_blocks_per_sm = 0;
     double dmma_growth = sri::kDmmaGrowthDefault;
-    bool use_dmma = false;       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
+    bool use_dmma = false;
+    int stage_impl = 0;          // N <= 16 separate-stage entry points: 0 = measured best per stage (position, couple: TMA-staged;
+                                 // stress: direct loads), 1 = SRI_STAGE_IMPL=tma everywhere, 2 = SRI_STAGE_IMPL=ldg everywhere       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
     // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
     int* d_list[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t list_cap[4] = {0, 0, 0, 0};
@@ -573,6 +577,67 @@ int launch_stage_dmma(sri_context* h, const sri::FusedParams& p) {
     return SRI_OK;
 }
 
+// Separate-stage entry points for N <= 16: whole tiles of 8 rods through the TMA-staged kernel when every pointer is
+// 16-byte aligned, the ragged tail (and unaligned calls) through the direct-load kernel.
+template <int STAGE>
+int launch_stage(sri_context* h, const sri::FusedParams& p_in) {
+    if (p_in.batch <= 0) return SRI_OK;
+    sri::FusedParams p = p_in;
+    const int M = p.M, N = p.N;
+    const long long tiles = p.batch / 8;
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const double* load = (STAGE == sri::kStageStress) ? p.fbar : p.lbar;
+    const double* tip = (STAGE == sri::kStageStress) ? p.F_tip : p.M_tip;
+    double* out = (STAGE == sri::kStagePosition) ? p.r : (STAGE == sri::kStageStress ? p.n : p.m);
+    const bool aligned = al(p.Qin) && al(p.nin) && al(p.Gamma) && al(load) && al(tip) && al(p.q0) && al(p.r0) && al(out);
+    // stress reads [3][16] stacks whose rows are 128-byte aligned: direct loads are already sector-exact there (92 % of HBM
+    // against 83 % through shared memory); position / couple read 15-double rows and gain 5 % / 37 % from the staging
+    const bool want_tma = h->stage_impl == 1 || (h->stage_impl == 0 && STAGE != sri::kStageStress);
+    if (!want_tma || tiles == 0 || !aligned) return launch_stage_dmma<STAGE>(h, p);
+    sri::StageTmaLayout L{};
+    int off = 0;
+    auto put = [&](bool present, int bytes) { if (!present) return -1; const int o = off; off += bytes; return o; };
+    L.q = put(STAGE != sri::kStageStress, 8 * 4 * M * 8);
+    L.nin = put(STAGE == sri::kStageCouple, 8 * 3 * M * 8);
+    L.gam = put(STAGE != sri::kStageStress && p.Gamma, 8 * 3 * N * 8);
+    L.load = put(STAGE != sri::kStagePosition && load, 8 * 3 * N * 8);
+    L.tip = put(STAGE != sri::kStagePosition, 192);
+    L.q0 = put(STAGE == sri::kStageCouple && p.q0, 256);
+    L.r0 = put(STAGE == sri::kStagePosition && p.r0, 192);
+    L.in_bytes = off;
+    L.out = 2 * off;
+    L.warp_bytes = 2 * off + 8 * 3 * M * 8;
+    const size_t smem = (size_t)sri::kStageTmaWarps * L.warp_bytes;
+    SRI_CUDA(cudaFuncSetAttribute(sri::stage_tma_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::stage_tma_kernel<STAGE>, 32 * sri::kStageTmaWarps, smem));
+    if (occ < 1) return launch_stage_dmma<STAGE>(h, p);
+    const long long want = (tiles + sri::kStageTmaWarps - 1) / sri::kStageTmaWarps;
+    const long long cap = (long long)h->sm_count * occ;
+    sri::stage_tma_kernel<STAGE><<<(int)(want < cap ? want : cap), 32 * sri::kStageTmaWarps, smem, h->stream>>>(p, L, tiles);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    const long long done = tiles * 8;
+    if (done < p.batch) {
+        sri::FusedParams t = p;
+        t.batch = p.batch - done;
+        if (t.Qin) t.Qin += done * 4 * M;
+        if (t.nin) t.nin += done * 3 * M;
+        if (t.Gamma) t.Gamma += done * 3 * N;
+        if (t.fbar) t.fbar += done * 3 * N;
+        if (t.lbar) t.lbar += done * 3 * N;
+        if (t.F_tip) t.F_tip += done * 3;
+        if (t.M_tip) t.M_tip += done * 3;
+        if (t.q0) t.q0 += done * 4;
+        if (t.r0) t.r0 += done * 3;
+        if (t.r) t.r += done * 3 * M;
+        if (t.n) t.n += done * 3 * M;
+        if (t.m) t.m += done * 3 * M;
+        return launch_stage_dmma<STAGE>(h, t);
+    }
+    return SRI_OK;
+}
+
 int check_handle(sri_handle h) {
     if (!h) return fail(SRI_ERR_INVALID_ARGUMENT, "null handle");
     cudaError_t e = cudaSetDevice(h->device);
@@ -774,6 +839,7 @@ int sri_create(int N, int device, sri_handle* out) {
     {
         const char* impl = std::getenv("SRI_FUSED16_IMPL");
         h->use_dmma = !(impl && std::strcmp(impl, "scalar") == 0);
+        if (const char* si = std::getenv("SRI_STAGE_IMPL")) h->stage_impl = std::strcmp(si, "tma") == 0 ? 1 : (std::strcmp(si, "ldg") == 0 ? 2 : 0);
         if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
     }
     *out = h;
@@ -906,7 +972,7 @@ int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const d
     SRI_TRY(st.in(Gamma, (size_t)batch * 3 * N, &p.Gamma));
     SRI_TRY(st.in(r0, (size_t)batch * 3, &p.r0));
     SRI_TRY(st.out(r, (size_t)batch * 3 * M, &p.r));
-    if (h->R == 0) SRI_TRY(launch_stage_dmma<sri::kStagePosition>(h, p));
+    if (h->R == 0) SRI_TRY(launch_stage<sri::kStagePosition>(h, p));
     else SRI_TRY(launch_fused16<false>(h, p));
     return st.finish();
 }
@@ -928,7 +994,7 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
         g_launches.fetch_add(1);
         SRI_CUDA(cudaGetLastError());
     } else if (h->R == 0) {
-        SRI_TRY(launch_stage_dmma<sri::kStageStress>(h, p));
+        SRI_TRY(launch_stage<sri::kStageStress>(h, p));
     } else {
         SRI_TRY(launch_fused16<false>(h, p));
     }
@@ -952,7 +1018,7 @@ int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const dou
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     p.F_tip = p.M_tip;  // unused when nin is given; keeps the pointer valid
     SRI_TRY(st.out(m, (size_t)batch * 3 * M, &p.m));
-    if (h->R == 0) SRI_TRY(launch_stage_dmma<sri::kStageCouple>(h, p));
+    if (h->R == 0) SRI_TRY(launch_stage<sri::kStageCouple>(h, p));
     else SRI_TRY(launch_fused16<false>(h, p));
     return st.finish();
 }

@@ -111,6 +111,36 @@ def test_separate_stage_calls_match_fused(h16, oracle16, torch_mod):
         assert rel_err(val.cpu().numpy(), ref[name]) <= TOL, name
 
 
+@pytest.mark.parametrize("impl", ["tma", "ldg"])
+@pytest.mark.parametrize("N,B", [(16, 1003), (16, 7), (11, 260)])
+def test_stage_kernels_tma_and_direct(monkeypatch, sri_lib, make_oracle, torch_mod, impl, N, B):
+    """Separate-stage entry points, N <= 16: the TMA-staged kernels (whole tiles of 8 rods through cp.async.bulk + mbarrier,
+    ragged tail through the direct-load kernel) and the direct-load kernels, all optional inputs, against the oracle."""
+    o = make_oracle(N)
+    rng = np.random.default_rng(N + B)
+    K, F, Mt, fb = o.generate_rods(17, 5, B)
+    q0 = rng.normal(size=(B, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    r0 = rng.normal(size=(B, 3))
+    Gamma = np.concatenate([1 + 0.1 * rng.normal(size=(B, 1, N)), 0.1 * rng.normal(size=(B, 2, N))], axis=1)
+    lbar = rng.normal(size=(B, 3, N))
+    ref = o.integrate_all(K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fb, lbar=lbar)
+    h = _handle_with_env(monkeypatch, N, SRI_STAGE_IMPL=impl)
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    try:
+        Q = h.integrate_quaternions(t(K), q0=t(q0))
+        r = h.integrate_position(Q, Gamma=t(Gamma), r0=t(r0))
+        n = h.integrate_stress(t(F), fbar=t(fb))
+        m = h.integrate_couple(Q, n, t(Mt), q0=t(q0), Gamma=t(Gamma), lbar=t(lbar))
+        # an unaligned view (odd rod offset of a [3][M] stack) must fall back to the direct-load kernel
+        m2 = h.integrate_couple(Q[1:], n[1:], t(Mt)[1:], q0=t(q0)[1:], Gamma=t(Gamma)[1:], lbar=t(lbar)[1:])
+        h.synchronize()
+    finally:
+        h.close()
+    for name, val in (("r", r), ("n", n), ("m", m)):
+        assert rel_err(val.cpu().numpy(), ref[name]) <= TOL, (impl, name)
+    assert rel_err(m2.cpu().numpy(), ref["m"][1:]) <= TOL
+
+
 def test_host_buffers_through_c_abi(h16, oracle16):
     """Plain host (numpy) buffers: the library stages them itself."""
     B = 300
