@@ -39,6 +39,7 @@ class StaticShapeSolver:
         self.H = tuple(float(v) for v in H_diag)
         self.ne = int(ne)
         self.fd_step = float(fd_step)
+        self._cache = {}
 
     # -- one evaluation of g(qe): 4 kernel launches
     def residual(self, qe, F_tip, M_tip, K0=None, work=None):
@@ -50,32 +51,82 @@ class StaticShapeSolver:
         g = h.project_onto_modes(rho, self.ne, out=None if work is None else work["g"])
         return g
 
-    def solve(self, F_tip, M_tip, qe0=None, K0=None, tol: float = 1e-10, max_iter: int = 30, group=None):
-        """Newton iteration until the GLOBAL rms of g over all ranks' rods is below tol.  Returns (qe, NewtonReport)."""
-        h, ne = self.h, self.ne
+    # -- persistent buffers (and the captured iteration) for one problem shape
+    def _workspace(self, B: int, dev, has_K0: bool):
+        key = (B, dev.index, has_K0)
+        ws = self._cache.get(key)
+        if ws is None:
+            h, n, f64 = self.h, 3 * self.ne, torch.float64
+            N, M = h.N, h.M
+            e = lambda *shape: torch.empty(shape, dtype=f64, device=dev)
+            ws = {"K": e(B, 3, N), "Q": e(B, 4, M), "m": e(B, 3, M), "rho": e(B, 3, N), "g": e(B, n),
+                  "F": e(B, 3), "Mt": e(B, 3), "K0": e(B, 3, N) if has_K0 else None,
+                  "qe": e(B, n), "g0": e(B, n), "J": e(B, n, n), "qp": e(B, n), "delta": e(B, n),
+                  "red": torch.zeros(2, dtype=f64, device=dev), "graph": None, "warmed": False}
+            self._cache.clear()  # one shape at a time: the buffers of a 10^6-rod problem are not small
+            self._cache[key] = ws
+        return ws
+
+    def _evaluate(self, ws):
+        """g0 <- g(qe) and red <- [sum g0^2, max |g0|] (this rank's rods)."""
+        g0, red = ws["g0"], ws["red"]
+        g0.copy_(self.residual(ws["qe"], ws["F"], ws["Mt"], ws["K0"], ws))
+        red[0] = (g0 * g0).sum()
+        red[1] = g0.abs().max() if g0.numel() else 0.0
+
+    def _iteration(self, ws):
+        """One Newton iteration on static buffers only (capturable): forward-difference Jacobian (3 ne integrations of
+        the whole batch), batched per-rod solve, update, residual of the new iterate."""
+        qe, qp, g0, J = ws["qe"], ws["qp"], ws["g0"], ws["J"]
+        for d in range(3 * self.ne):
+            qp.copy_(qe)
+            qp[:, d] += self.fd_step
+            gd = self.residual(qp, ws["F"], ws["Mt"], ws["K0"], ws)
+            J[:, :, d] = (gd - g0) / self.fd_step
+        self.h.solve_small_batched(J, g0, out=ws["delta"])  # per-rod n x n Newton system
+        qe -= ws["delta"]
+        self._evaluate(ws)
+
+    def _capture(self, ws, dev):
+        """Capture one iteration (~12 launches per integration, 3 ne + 1 integrations) into a CUDA graph: the loop is
+        launch-bound at 10^5 rods per GPU (0.44 ms of kernel per integration against ~1.2 ms of launches)."""
+        h = self.h
+        was_explicit, was_stream = h._explicit_stream, torch.cuda.current_stream(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            h.set_stream(torch.cuda.current_stream(dev))  # this library's launches join the capture
+            self._iteration(ws)
+        h.set_stream(was_stream if was_explicit else None)
+        ws["graph"] = graph
+
+    def solve(self, F_tip, M_tip, qe0=None, K0=None, tol: float = 1e-10, max_iter: int = 30, group=None,
+              use_graph: bool = True):
+        """Newton iteration until the GLOBAL rms of g over all ranks' rods is below tol.  Returns (qe, NewtonReport).
+
+        The first iteration of a new problem shape runs eagerly, the second is captured into a CUDA graph, every later
+        one -- and every iteration of later solve() calls with the same batch size -- replays it."""
+        ne = self.ne
         B = F_tip.shape[0]
         n = 3 * ne
         dev, f64 = F_tip.device, torch.float64
-        qe = torch.zeros((B, n), dtype=f64, device=dev) if qe0 is None else qe0.clone()
-        N, M = h.N, h.M
-        work = {"K": torch.empty((B, 3, N), dtype=f64, device=dev), "Q": torch.empty((B, 4, M), dtype=f64, device=dev),
-                "m": torch.empty((B, 3, M), dtype=f64, device=dev), "rho": torch.empty((B, 3, N), dtype=f64, device=dev),
-                "g": torch.empty((B, n), dtype=f64, device=dev)}
-        g0 = torch.empty((B, n), dtype=f64, device=dev)
-        J = torch.empty((B, n, n), dtype=f64, device=dev)
-        qp = torch.empty_like(qe)
-        delta = torch.empty_like(qe)
-        red = torch.zeros(2, dtype=f64, device=dev)
+        ws = self._workspace(B, dev, K0 is not None)
+        ws["F"].copy_(F_tip)
+        ws["Mt"].copy_(M_tip)
+        if K0 is not None:
+            ws["K0"].copy_(K0)
+        if qe0 is None:
+            ws["qe"].zero_()
+        else:
+            ws["qe"].copy_(qe0)
+        red = ws["red"]
         count = torch.tensor([float(B * n)], dtype=f64, device=dev)
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             torch.distributed.all_reduce(count, group=group)
         total_dof = float(count.item())
         rep = NewtonReport(iterations=0, converged=False)
+        self._evaluate(ws)
+        rep.integrations += 1
         for it in range(max_iter + 1):
-            g0.copy_(self.residual(qe, F_tip, M_tip, K0, work))
-            rep.integrations += 1
-            red[0] = (g0 * g0).sum()
-            red[1] = g0.abs().max() if B else 0.0
             allreduce_residual(red, group)                     # the only collective: 16 bytes per iteration
             rms = float((red[0] / total_dof).sqrt().item())
             rep.rms_history.append(rms)
@@ -85,13 +136,13 @@ class StaticShapeSolver:
                 break
             if it == max_iter:
                 break
-            for d in range(n):                                  # forward-difference Jacobian, column d
-                qp.copy_(qe)
-                qp[:, d] += self.fd_step
-                gd = self.residual(qp, F_tip, M_tip, K0, work)
-                J[:, :, d] = (gd - g0) / self.fd_step
-                rep.integrations += 1
-            h.solve_small_batched(J, g0, out=delta)             # per-rod n x n Newton system
-            qe -= delta
+            if use_graph and B > 0 and ws["graph"] is None and ws["warmed"]:
+                self._capture(ws, dev)
+            if use_graph and ws["graph"] is not None:
+                ws["graph"].replay()
+            else:
+                self._iteration(ws)
+                ws["warmed"] = True
             rep.iterations += 1
-        return qe, rep
+            rep.integrations += n + 1
+        return ws["qe"].clone(), rep

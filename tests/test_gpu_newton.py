@@ -111,3 +111,34 @@ def test_newton_tip_force_matches_cpu_replica(h16, oracle16, torch_mod):
     assert np.abs(qe.cpu().numpy() - q).max() < 1e-8
     # and the converged shape is a real equilibrium: the nodal residual is at discretisation level
     assert np.abs(g_cpu(qe.cpu().numpy())).max() < 1e-9
+
+
+def test_newton_cuda_graph_replay_equals_eager_and_is_reused(h16, torch_mod):
+    """The captured iteration (CUDA graph) must reproduce the eager iteration bit for bit, and a second solve with the same
+    batch size must replay the cached graph from its first iteration on."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200.newton import StaticShapeSolver
+    B, ne = 500, 3
+    rng = np.random.default_rng(5)
+    F = np.zeros((B, 3)); F[:, 2] = -rng.uniform(0.1, 2.0, size=B)
+    Mt = rng.uniform(-0.1, 0.1, size=(B, 3))
+    tF, tM = torch_mod.from_numpy(F).cuda(), torch_mod.from_numpy(Mt).cuda()
+    eager = StaticShapeSolver(h16, (1.0, 1.0, 0.77), ne=ne)
+    q_e, rep_e = eager.solve(tF, tM, use_graph=False)
+    graphed = StaticShapeSolver(h16, (1.0, 1.0, 0.77), ne=ne)
+    q_g, rep_g = graphed.solve(tF, tM)
+    assert rep_e.converged and rep_g.converged and rep_g.iterations == rep_e.iterations >= 3
+    assert torch_mod.equal(q_e, q_g)
+    assert rep_g.rms_history == rep_e.rms_history
+    ws = next(iter(graphed._cache.values()))
+    assert ws["graph"] is not None
+    # second solve, other loads, same shape: graph reused (no new capture), still correct
+    g_before = ws["graph"]
+    q2_g, rep2_g = graphed.solve(tF * 0.5, tM)
+    q2_e, rep2_e = eager.solve(tF * 0.5, tM, use_graph=False)
+    assert next(iter(graphed._cache.values()))["graph"] is g_before
+    assert rep2_g.converged and torch_mod.equal(q2_e, q2_g)
+    # the integrator handle is usable outside the graph afterwards
+    K = torch_mod.zeros((4, 3, 16), dtype=torch_mod.float64, device="cuda")
+    out = h16.integrate_all(K, tF[:4], tM[:4])
+    h16.synchronize()
+    assert np.isfinite(out["Q"].cpu().numpy()).all()
