@@ -209,6 +209,55 @@ def test_T13_dead_load_couple(make_oracle, N, tol):
     assert np.abs(out["m"][0] - m_exact).max() < tol
 
 
+@pytest.mark.parametrize("N,tol", [(16, 2e-6), (32, 1e-11), (48, 1e-11)])
+def test_T10_global_vs_local_frame_statics(make_oracle, N, tol):
+    """the global-frame stages 3-4 (rod_modeling.pdf 1.17-1.18), rotated into the body frame, must solve the
+    local-frame statics Lambda' = ad^T_xi Lambda - Fbar (eq. 1.29 / 2.18), i.e. N' = -K^ N - R^T fbar and
+    C' = -K^ C - Gamma^ N - R^T lbar.  The local ODE is collocated here independently (numpy, strain-dependent 3M x 3M
+    operator with the tip node eliminated); agreement is to discretisation error, which pins the sign conventions of
+    stages 3-4 and of the wrench_local output."""
+    o = make_oracle(N)
+    M = N - 1
+    rng = np.random.default_rng(N)
+    K, F, Mt, fb = o.generate_rods(0x5EED, 3, 3)
+    x = o.chebyshev_points()
+    fbar = fb + 0.3 * rng.normal(size=(3, 3, 1)) * np.sin(2 * x)[None, None, :] + 0.2 * rng.normal(size=(3, 3, 1)) * x[None, None, :]
+    lbar = 0.2 * rng.normal(size=(3, 3, 1)) * np.cos(x)[None, None, :]
+    q0 = rng.normal(size=(3, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    out = o.integrate_all(K, F, Mt, q0=q0, fbar=fbar, lbar=lbar)
+    lam = o.wrench_local(out["Q"], out["n"], out["m"], F, Mt, q0=q0)     # [B][6][N], couple first
+    Dn = o.operator(0)
+    D_TT, D_TI = Dn[1:, 1:], Dn[1:, 0]
+
+    def rot(q):
+        w, x, y, z = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    def skew(v):
+        return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+    for b in range(3):
+        R = [rot(out["Q"][b][:, i]) if i < M else rot(q0[b]) for i in range(N)]
+        A = np.kron(D_TT, np.eye(3))
+        for i in range(1, N):
+            A[3 * (i - 1):3 * i, 3 * (i - 1):3 * i] += skew(K[b][:, i])
+        # internal force
+        N0 = R[0].T @ F[b]
+        rhs = np.concatenate([-R[i].T @ fbar[b][:, i] for i in range(1, N)]) - np.kron(D_TI, N0)
+        Nloc = np.linalg.solve(A, rhs).reshape(M, 3)
+        # internal couple (Gamma = e1)
+        C0 = R[0].T @ Mt[b]
+        G = skew(np.array([1.0, 0.0, 0.0]))
+        rhs = np.concatenate([-G @ Nloc[i - 1] - R[i].T @ lbar[b][:, i] for i in range(1, N)]) - np.kron(D_TI, C0)
+        Cloc = np.linalg.solve(A, rhs).reshape(M, 3)
+        scale = max(np.abs(Nloc).max(), np.abs(Cloc).max())
+        assert np.abs(lam[b][3:, 1:].T - Nloc).max() <= tol * scale, (N, "N")
+        assert np.abs(lam[b][:3, 1:].T - Cloc).max() <= tol * scale, (N, "C")
+        assert np.abs(lam[b][3:, 0] - N0).max() <= 1e-15 and np.abs(lam[b][:3, 0] - C0).max() <= 1e-15
+
+
 # ---- independent restatements -----------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("N", [8, 16, 32])
