@@ -209,7 +209,7 @@ def test_T13_dead_load_couple(make_oracle, N, tol):
     assert np.abs(out["m"][0] - m_exact).max() < tol
 
 
-@pytest.mark.parametrize("N,tol", [(16, 2e-6), (32, 1e-11), (48, 1e-11)])
+@pytest.mark.parametrize("N,tol", [(16, 1e-7), (32, 1e-12), (48, 1e-12)])  # observed: 1e-8, 1e-13, 1e-13
 def test_T10_global_vs_local_frame_statics(make_oracle, N, tol):
     """the global-frame stages 3-4 (rod_modeling.pdf 1.17-1.18), rotated into the body frame, must solve the
     local-frame statics Lambda' = ad^T_xi Lambda - Fbar (eq. 1.29 / 2.18), i.e. N' = -K^ N - R^T fbar and
