@@ -1,4 +1,9 @@
-// sri_fused16.cuh -- fused four-stage kernel for N <= 16 Chebyshev nodes (M = N-1 <= 15 unknown nodes).
+// sri_fused16.cuh -- row-pivoting fused four-stage kernel for N <= 16 Chebyshev nodes (M = N-1 <= 15 unknown nodes).
+//
+// Role: second pass of the N <= 16 path.  The tensor-core kernel (sri_fused16_dmma.cuh) eliminates in static pivot order
+// and hands the rods that fail its growth check back to this kernel through FusedParams::rod_list; with
+// SRI_FUSED16_IMPL=scalar it runs the whole batch (1.97e8 rods/s on one B200).  FusedParams and the small PTX helpers
+// shared by all fused kernels live here too.
 //
 // Mapping: TWO rods per warp.  Lanes 0..15 own rod A, lanes 16..31 rod B; lane `row` of a half-warp owns row
 // `row` of that rod's M x M quaternion collocation operator (M quaternions + the right-hand side = 64 doubles,
@@ -12,9 +17,9 @@
 //     so every serial FP64 chain on the elimination's critical path is kept as short as possible (tree-shaped
 //     products, branch-free Newton reciprocal) and the pivot search / reciprocal of step k+1 is issued before the
 //     bulk update of step k so that it hides behind this warp's own DFMA stream;
-//   * a row lives in ONE lane, and getting it out costs the same LSU time whichever way (8.4 cycles per quaternion
-//     for a 2-lane shared-memory store + 4.2 for the loads, 8.2 for eight SHFL.IDX); shuffles need no barrier and
-//     keep each elimination step a single basic block the scheduler can software-pipeline, so shuffles it is;
+//   * a row lives in ONE lane, and getting it out costs LSU time whichever way (8.4 SM-cycles per quaternion for a 2-lane
+//     shared-memory store + 4.2 for the loads, 8.2 for eight SHFL.IDX); the shared-memory form ships because the shuffle
+//     form (-DSRI_BCAST_SHFL=1) pushes the hot code past the instruction cache;
 //   * per-rod inputs that are only needed after the elimination are prefetched with cp.async at the top of the
 //     iteration, as are the next pair's strain samples.
 #pragma once
@@ -150,12 +155,6 @@ __device__ __forceinline__ unsigned segment_max16(unsigned key) {
 #ifndef SRI_BCAST_SHFL
 #define SRI_BCAST_SHFL 0  // 0: pivot row through shared memory; 1: SHFL.IDX
 #endif
-#ifndef SRI_WINDOWS
-#define SRI_WINDOWS 4  // number of window-size classes (elimination loop bodies): 4, 3 or 2
-#endif
-#ifndef SRI_GROUP
-#define SRI_GROUP 3  // quaternion updates interleaved level by level
-#endif
 
 // One Gauss-Jordan step over the quaternions with implicit row pivoting, ROLLED form.
 //
@@ -164,8 +163,9 @@ __device__ __forceinline__ unsigned segment_max16(unsigned key) {
 // So the row is kept in a sliding window instead: slot 0 always holds the pivot column of the current step, every
 // update writes its result one slot down (c[j-1] = c[j] - u_j (x) m; the shift costs no instruction), and the same
 // body serves several steps.  L = number of window slots the body touches; a body may run while the live width
-// 15-k is <= L (the slots beyond it hold zeros and stay zero).  Four bodies (L = 15, 11, 7, 3) cost 17 % more
-// quaternion updates than the exact triangle and fit the whole kernel in the instruction cache.
+// 15-k is <= L (the slots beyond it hold zeros and stay zero).  Four bodies (L = 15, 11, 7, 3; two or three bodies
+// measured 1-6 % slower) cost 17 % more quaternion updates than the exact triangle and fit the whole kernel in the
+// instruction cache.
 //
 //   equations:  sum_j Q_j (x) c_ij = b_i.   Row i takes  c_ij -= u_j (x) m_i  with u = pivot row and
 //   m_i = c_pk^-1 (x) c_ik; the pivot row takes m_p = 1 - c_pk^-1, which normalises it with the same update.
@@ -250,7 +250,6 @@ __device__ __forceinline__ void gauss_jordan16(quat (&c)[15], quat& b, int M, in
     key = segment_max16(key);
     int k = 0;
     // the body is chosen by the live width M - k, so a short system (N < 16) starts directly with a small window
-#if SRI_WINDOWS == 4
 #pragma unroll 1
     for (; M - k > 11; ++k) gj_step_rolled<15, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
 #pragma unroll 1
@@ -259,19 +258,6 @@ __device__ __forceinline__ void gauss_jordan16(quat (&c)[15], quat& b, int M, in
     for (; M - k > 3; ++k) gj_step_rolled<7, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
 #pragma unroll 1
     for (; M - k > 0; ++k) gj_step_rolled<3, 3>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
-#elif SRI_WINDOWS == 3
-#pragma unroll 1
-    for (; M - k > 10; ++k) gj_step_rolled<15, 4>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
-#pragma unroll 1
-    for (; M - k > 5; ++k) gj_step_rolled<10, 4>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
-#pragma unroll 1
-    for (; M - k > 0; ++k) gj_step_rolled<5, 5>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
-#else
-#pragma unroll 1
-    for (; M - k > 7; ++k) gj_step_rolled<15, 7>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
-#pragma unroll 1
-    for (; M - k > 0; ++k) gj_step_rolled<7, 7>(c, b, k, M - k, row, pbuf, used, mycol, sing, key, cand);
-#endif
 }
 
 // out_c = sum_j T[j*16+row] * v[j][c], c = 0..2, with three interleaved partial sums per component so that the

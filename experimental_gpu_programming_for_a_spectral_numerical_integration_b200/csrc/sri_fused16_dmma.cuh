@@ -13,8 +13,9 @@
 //      Cr -= [Rmat(c_0k); Rmat(c_1k); ...; Rmat(c_kk - 1); ...] U'      (rank-4 update: 8 x 2 DMMAs, k = 4 exactly)
 // 4 x 4 real blocks appear only in the A operand (the multipliers); the matrix itself stays in quaternion (4-vector)
 // form, so the DMMAs execute exactly the 16 FMAs per quaternion multiply-add of the scalar kernel.
-// Per step the LSU only moves the pivot row into B-fragment layout (2 SHFL.64 per column tile), the pivot element
-// to every lane (4 SHFL.64) and the pivot column into A-fragment layout (1 SHFL.64 per row tile).
+// Per step the LSU only moves the pivot row into B-fragment layout (2 SHFL.64 per column tile), one component of the
+// pivot element and its squared norm to every lane (2 SHFL.64) and the pivot column into A-fragment layout (1 SHFL.64
+// per row tile).  Stages 2-4 are [16 x 16] x [16 x 3] DMMA contractions in the same warp (Q never leaves the SM).
 //
 // Pivoting: the order is static (pivot k = row k).  The left-preconditioned operator I - 1/2 S diag(kappa) has
 // |c_kk| >= 1 and measured sub-diagonal growth <= 0.15 for |K| <= 10 and <= 2.4 for |K| <= 300, so a search would
