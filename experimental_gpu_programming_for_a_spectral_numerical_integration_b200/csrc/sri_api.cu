@@ -20,6 +20,13 @@
 #include "sri_stage_tma.cuh"
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
+
+// <row tiles per warp, column tiles, warps> of the N <= 32 instantiation of the multi-warp DMMA kernel
+#ifndef SRI_T32_RT
+#define SRI_T32_RT 4
+#define SRI_T32_W 4
+#endif
+#define SRI_T32 SRI_T32_RT, 4, SRI_T32_W
 #include "sri_host_math.hpp"
 
 namespace {
@@ -407,8 +414,8 @@ int launch_generic(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
         const long long dcap = (long long)h->sm_count * h->dmma_blocks_per_sm;
         const int dgrid = (int)(p.batch < dcap ? p.batch : dcap);
         if (h->R == 32) {
-            using Cfg = sri::TiledDmmaCfg<4, 4, 4>;
-            sri::tiled_dmma_kernel<4, 4, 4><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
+            using Cfg = sri::TiledDmmaCfg<SRI_T32>;
+            sri::tiled_dmma_kernel<SRI_T32><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
         } else {
             using Cfg = sri::TiledDmmaCfg<2, 8, 16>;
             sri::tiled_dmma_kernel<2, 8, 16><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
@@ -783,9 +790,9 @@ int sri_create(int N, int device, sri_handle* out) {
             SRI_CUDA(cudaMalloc(&h->d_ops2, sizeof(double) * t2.size()));
             SRI_CUDA(cudaMemcpy(h->d_ops2, t2.data(), sizeof(double) * t2.size(), cudaMemcpyHostToDevice));
             if (R == 32) {
-                using Cfg = sri::TiledDmmaCfg<4, 4, 4>;
-                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-                SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<4, 4, 4>, Cfg::threads, Cfg::smem_bytes));
+                using Cfg = sri::TiledDmmaCfg<SRI_T32>;
+                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<SRI_T32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+                SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<SRI_T32>, Cfg::threads, Cfg::smem_bytes));
             } else {
                 using Cfg = sri::TiledDmmaCfg<2, 8, 16>;
                 SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));

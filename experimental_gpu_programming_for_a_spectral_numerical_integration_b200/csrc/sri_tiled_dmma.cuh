@@ -30,6 +30,7 @@ struct TiledDmmaCfg {
     static constexpr int QR = 2 * RT * W;   // quaternion row capacity (32 / 64)
     static constexpr int NC = 8 * CT;       // columns incl. the right-hand side (32 / 64)
     static_assert(QR == NC, "square capacity");
+    static_assert(W % 4 == 0, "the compile-time local index of the pivot tile needs W to be a multiple of 4");
     static constexpr int RS = NC + 4;       // row stride of the [4][NC] right-hand sides (rows on disjoint banks)
     static constexpr int MT = QR / 8;       // m-tiles of the stage operators
     static constexpr int KT = NC / 4;       // k-tiles
@@ -55,8 +56,11 @@ struct TiledDmmaCfg {
     static constexpr size_t smem_bytes = (size_t)total * sizeof(double);
 };
 
+#ifndef SRI_T32_MINBLOCKS
+#define SRI_T32_MINBLOCKS 5  // measured: 4 CTAs/SM 2.87e7, 5 (94 registers, no spills) 3.01e7, 6 (spills) 2.86e7 rods/s at N = 32
+#endif
 template <int RT, int CT, int W>
-__global__ void __launch_bounds__(32 * W, (W == 4 ? 4 : 1)) tiled_dmma_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(32 * W, (W == 4 ? SRI_T32_MINBLOCKS : (W == 8 ? 3 : 1))) tiled_dmma_kernel(const FusedParams p) {
     using C = TiledDmmaCfg<RT, CT, W>;
     constexpr int NC = C::NC, QR = C::QR, RS = C::RS, KT = C::KT, MT = C::MT;
     extern __shared__ __align__(16) double smem[];
@@ -118,9 +122,12 @@ __global__ void __launch_bounds__(32 * W, (W == 4 ? 4 : 1)) tiled_dmma_kernel(co
         }
         if (tid < N && p.Gamma)
             for (int c = 0; c < 3; ++c) cp_async8(smem + C::gam + NC * c + tid, p.Gamma + (rod * 3 + c) * N + tid);
-        if (tid >= 64 && tid < 67) { if (p.F_tip) cp_async8(smem + C::fbs + RS * (tid - 64) + NC - 1, p.F_tip + rod * 3 + tid - 64); }
-        else if (tid >= 68 && tid < 71) { if (p.M_tip) cp_async8(smem + C::xs + RS * (tid - 68) + NC - 1, p.M_tip + rod * 3 + tid - 68); }
-        else if (tid >= 72 && tid < 75) { if (p.r0) cp_async8(smem + C::bs + RS * (tid - 72) + NC - 1, p.r0 + rod * 3 + tid - 72); }
+        {
+            const int t3 = C::threads - 1 - tid;  // the last threads of the CTA carry the three boundary vectors
+            if (t3 >= 0 && t3 < 3) { if (p.F_tip) cp_async8(smem + C::fbs + RS * t3 + NC - 1, p.F_tip + rod * 3 + t3); }
+            else if (t3 >= 4 && t3 < 7) { if (p.M_tip) cp_async8(smem + C::xs + RS * (t3 - 4) + NC - 1, p.M_tip + rod * 3 + t3 - 4); }
+            else if (t3 >= 8 && t3 < 11) { if (p.r0) cp_async8(smem + C::bs + RS * (t3 - 8) + NC - 1, p.r0 + rod * 3 + t3 - 8); }
+        }
         if (rod + gridDim.x < p.batch) prefetch_K(rod + gridDim.x, cur ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
@@ -292,34 +299,48 @@ __global__ void __launch_bounds__(32 * W, (W == 4 ? 4 : 1)) tiled_dmma_kernel(co
         }
         if (p.r || p.n || p.m) {
             __syncthreads();
-            double acc0 = 0.0, acc1 = 0.0;
+            // m-tiles of the stage operators are dealt to the warps: mt = w, w + W, ...
+            constexpr int MPW = (MT + W - 1) / W;
+            double acc0[MPW], acc1[MPW];
             auto contract = [&](const double* at, const double* rhs, int kt0) {
-                acc0 = 0.0; acc1 = 0.0;
-                const double* a = at + (w * KT) * 32 + lane;
                 const double* b = rhs + offb;
+#pragma unroll
+                for (int q = 0; q < MPW; ++q) {
+                    acc0[q] = 0.0; acc1[q] = 0.0;
+                    const int mt = w + q * W;
+                    if (mt < MT) {
+                        const double* a = at + (mt * KT) * 32 + lane;
 #pragma unroll 4
-                for (int kt = kt0; kt < KT; ++kt) dmma(acc0, acc1, a[kt * 32], b[4 * kt]);
+                        for (int kt = kt0; kt < KT; ++kt) dmma(acc0[q], acc1[q], a[kt * 32], b[4 * kt]);
+                    }
+                }
             };
             auto store = [&](double* out) {
-                const int i = 8 * w + rho;
-                if (i < M) {
-                    if (cp == 0) { out[i] = acc0; out[M + i] = acc1; }
-                    else if (cp == 1) out[2 * M + i] = acc0;
+#pragma unroll
+                for (int q = 0; q < MPW; ++q) {
+                    const int i = 8 * (w + q * W) + rho;
+                    if (i < M) {
+                        if (cp == 0) { out[i] = acc0[q]; out[M + i] = acc1[q]; }
+                        else if (cp == 1) out[2 * M + i] = acc0[q];
+                    }
                 }
             };
-            if (w < MT) {
-                if (p.r) {
-                    contract(tabAS, smem + C::bs, 0);
-                    if (keep) store(p.r + rod * 3 * M);
-                }
-                if (p.n || p.m) {
-                    contract(tabAT, smem + C::fbs, p.fbar ? 0 : KT - 1);
-                    if (p.n && keep) store(p.n + rod * 3 * M);
-                    if (p.m) {
-                        double* nsv = smem + C::ns;
-                        const int i = 8 * w + rho;
-                        if (cp == 0) { nsv[i] = acc0; nsv[NC + i] = acc1; }
-                        else if (cp == 1) nsv[2 * NC + i] = acc0;
+            if (p.r) {
+                contract(tabAS, smem + C::bs, 0);
+                if (keep) store(p.r + rod * 3 * M);
+            }
+            if (p.n || p.m) {
+                contract(tabAT, smem + C::fbs, p.fbar ? 0 : KT - 1);
+                if (p.n && keep) store(p.n + rod * 3 * M);
+                if (p.m) {
+                    double* nsv = smem + C::ns;
+#pragma unroll
+                    for (int q = 0; q < MPW; ++q) {
+                        const int i = 8 * (w + q * W) + rho;
+                        if (i < QR) {
+                            if (cp == 0) { nsv[i] = acc0[q]; nsv[NC + i] = acc1[q]; }
+                            else if (cp == 1) nsv[2 * NC + i] = acc0[q];
+                        }
                     }
                 }
             }
@@ -338,10 +359,8 @@ __global__ void __launch_bounds__(32 * W, (W == 4 ? 4 : 1)) tiled_dmma_kernel(co
                     x[2 * RS] = fma(rp0, n1, fma(-rp1, n0, l2));
                 }
                 __syncthreads();
-                if (w < MT) {
-                    contract(tabAT, smem + C::xs, 0);
-                    if (keep) store(p.m + rod * 3 * M);
-                }
+                contract(tabAT, smem + C::xs, 0);
+                if (keep) store(p.m + rod * 3 * M);
             }
         }
         __syncthreads();  // scratch is reused by the next rod
