@@ -27,6 +27,11 @@
 #define SRI_T32_W 4
 #endif
 #define SRI_T32 SRI_T32_RT, 4, SRI_T32_W
+#ifndef SRI_T64_RT
+#define SRI_T64_RT 2
+#define SRI_T64_W 16
+#endif
+#define SRI_T64 SRI_T64_RT, 8, SRI_T64_W
 #include "sri_host_math.hpp"
 
 namespace {
@@ -417,8 +422,8 @@ int launch_generic(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
             using Cfg = sri::TiledDmmaCfg<SRI_T32>;
             sri::tiled_dmma_kernel<SRI_T32><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
         } else {
-            using Cfg = sri::TiledDmmaCfg<2, 8, 16>;
-            sri::tiled_dmma_kernel<2, 8, 16><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
+            using Cfg = sri::TiledDmmaCfg<SRI_T64>;
+            sri::tiled_dmma_kernel<SRI_T64><<<dgrid, Cfg::threads, Cfg::smem_bytes, stream>>>(p);
         }
         g_launches.fetch_add(1);
         SRI_CUDA(cudaGetLastError());
@@ -794,9 +799,9 @@ int sri_create(int N, int device, sri_handle* out) {
                 SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<SRI_T32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
                 SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<SRI_T32>, Cfg::threads, Cfg::smem_bytes));
             } else {
-                using Cfg = sri::TiledDmmaCfg<2, 8, 16>;
-                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-                SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<2, 8, 16>, Cfg::threads, Cfg::smem_bytes));
+                using Cfg = sri::TiledDmmaCfg<SRI_T64>;
+                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<SRI_T64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+                SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<SRI_T64>, Cfg::threads, Cfg::smem_bytes));
             }
             if (h->dmma_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
         }

@@ -60,7 +60,7 @@ struct TiledDmmaCfg {
 #define SRI_T32_MINBLOCKS 5  // measured: 4 CTAs/SM 2.87e7, 5 (94 registers, no spills) 3.01e7, 6 (spills) 2.86e7 rods/s at N = 32
 #endif
 template <int RT, int CT, int W>
-__global__ void __launch_bounds__(32 * W, (W == 4 ? SRI_T32_MINBLOCKS : (W == 8 ? 3 : 1))) tiled_dmma_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(32 * W, (W == 4 ? SRI_T32_MINBLOCKS : 1)) tiled_dmma_kernel(const FusedParams p) {
     using C = TiledDmmaCfg<RT, CT, W>;
     constexpr int NC = C::NC, QR = C::QR, RS = C::RS, KT = C::KT, MT = C::MT;
     extern __shared__ __align__(16) double smem[];
