@@ -17,6 +17,7 @@
 #include "sri_fused16_dmma.cuh"
 #include "sri_generic.cuh"
 #include "sri_stage_dmma.cuh"
+#include "sri_stage_generic.cuh"
 #include "sri_stage_tma.cuh"
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
@@ -650,6 +651,31 @@ int launch_stage(sri_context* h, const sri::FusedParams& p_in) {
     return SRI_OK;
 }
 
+// Separate-stage entry points for 17 <= N <= 64: streaming DMMA contraction against the fragment-ordered operator tables.
+template <int STAGE>
+int launch_stage_generic(sri_context* h, const sri::FusedParams& p_in) {
+    if (p_in.batch <= 0) return SRI_OK;
+    sri::FusedParams p = p_in;
+    p.ops2 = h->d_ops2;
+    const long long tiles = (p.batch + 7) / 8;
+    const long long want = (tiles + 3) / 4;
+    const size_t smem = (size_t)h->R * h->R * sizeof(double);
+    int occ = 0;
+    if (h->R == 32) {
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::stage_generic_kernel<STAGE, 32>, 128, smem));
+    } else {
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::stage_generic_kernel<STAGE, 64>, 128, smem));
+    }
+    if (occ < 1) return fail(SRI_ERR_CUDA, "stage kernel does not fit on this device");
+    const long long cap = (long long)h->sm_count * occ;
+    const int grid = (int)(want < cap ? want : cap);
+    if (h->R == 32) sri::stage_generic_kernel<STAGE, 32><<<grid, 128, smem, h->stream>>>(p);
+    else sri::stage_generic_kernel<STAGE, 64><<<grid, 128, smem, h->stream>>>(p);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
 int check_handle(sri_handle h) {
     if (!h) return fail(SRI_ERR_INVALID_ARGUMENT, "null handle");
     cudaError_t e = cudaSetDevice(h->device);
@@ -985,7 +1011,7 @@ int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const d
     SRI_TRY(st.in(r0, (size_t)batch * 3, &p.r0));
     SRI_TRY(st.out(r, (size_t)batch * 3 * M, &p.r));
     if (h->R == 0) SRI_TRY(launch_stage<sri::kStagePosition>(h, p));
-    else SRI_TRY(launch_fused16<false>(h, p));
+    else SRI_TRY(launch_stage_generic<sri::kStagePosition>(h, p));
     return st.finish();
 }
 
@@ -1008,7 +1034,7 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
     } else if (h->R == 0) {
         SRI_TRY(launch_stage<sri::kStageStress>(h, p));
     } else {
-        SRI_TRY(launch_fused16<false>(h, p));
+        SRI_TRY(launch_stage_generic<sri::kStageStress>(h, p));
     }
     return st.finish();
 }
@@ -1031,7 +1057,7 @@ int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const dou
     p.F_tip = p.M_tip;  // unused when nin is given; keeps the pointer valid
     SRI_TRY(st.out(m, (size_t)batch * 3 * M, &p.m));
     if (h->R == 0) SRI_TRY(launch_stage<sri::kStageCouple>(h, p));
-    else SRI_TRY(launch_fused16<false>(h, p));
+    else SRI_TRY(launch_stage_generic<sri::kStageCouple>(h, p));
     return st.finish();
 }
 

@@ -141,6 +141,37 @@ def test_stage_kernels_tma_and_direct(monkeypatch, sri_lib, make_oracle, torch_m
     assert rel_err(m2.cpu().numpy(), ref["m"][1:]) <= TOL
 
 
+@pytest.mark.parametrize("N,B", [(17, 130), (32, 257), (40, 33), (64, 101)])
+def test_high_resolution_stage_kernels(sri_lib, make_oracle, torch_mod, N, B):
+    """Separate-stage entry points for 17 <= N <= 64 (streaming DMMA contraction, csrc/sri_stage_generic.cuh): every
+    optional input, the no-load force stage, ragged tiles."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    o = make_oracle(N)
+    rng = np.random.default_rng(1000 + N)
+    K, F, Mt, fb = o.generate_rods(23, 9, B)
+    q0 = rng.normal(size=(B, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    r0 = rng.normal(size=(B, 3))
+    Gamma = np.concatenate([1 + 0.1 * rng.normal(size=(B, 1, N)), 0.1 * rng.normal(size=(B, 2, N))], axis=1)
+    lbar = rng.normal(size=(B, 3, N))
+    ref = o.integrate_all(K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fb, lbar=lbar)
+    ref0 = o.integrate_all(K, F, Mt)  # defaults: Gamma = e1, q0 = identity, no loads
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    with SpectralRodIntegrator(N, 0) as h:
+        Q = h.integrate_quaternions(t(K), q0=t(q0))
+        r = h.integrate_position(Q, Gamma=t(Gamma), r0=t(r0))
+        n = h.integrate_stress(t(F), fbar=t(fb))
+        m = h.integrate_couple(Q, n, t(Mt), q0=t(q0), Gamma=t(Gamma), lbar=t(lbar))
+        Qd = h.integrate_quaternions(t(K))
+        rd = h.integrate_position(Qd)
+        nd = h.integrate_stress(t(F))
+        md = h.integrate_couple(Qd, nd, t(Mt))
+        h.synchronize()
+    for name, val in (("r", r), ("n", n), ("m", m)):
+        assert rel_err(val.cpu().numpy(), ref[name]) <= TOL, (N, name, rel_err(val.cpu().numpy(), ref[name]))
+    for name, val in (("r", rd), ("n", nd), ("m", md)):
+        assert rel_err(val.cpu().numpy(), ref0[name]) <= TOL, (N, name, "defaults")
+
+
 def test_host_buffers_through_c_abi(h16, oracle16):
     """Plain host (numpy) buffers: the library stages them itself."""
     B = 300
