@@ -73,6 +73,8 @@ struct sri_context {
     int dmma_blocks_per_sm = 0;
     double dmma_growth = sri::kDmmaGrowthDefault;
     bool use_dmma = false;
+    size_t tma_smem[3] = {0, 0, 0};  // last shared-memory size configured per TMA stage kernel, and its occupancy
+    int tma_occ[3] = {0, 0, 0};
     int stage_impl = 0;          // N <= 16 separate-stage entry points: 0 = measured best per stage (position, couple: TMA-staged;
                                  // stress: direct loads), 1 = SRI_STAGE_IMPL=tma everywhere, 2 = SRI_STAGE_IMPL=ldg everywhere       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
     // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
@@ -621,9 +623,12 @@ int launch_stage(sri_context* h, const sri::FusedParams& p_in) {
     L.out = 2 * off;
     L.warp_bytes = 2 * off + 8 * 3 * M * 8;
     const size_t smem = (size_t)sri::kStageTmaWarps * L.warp_bytes;
-    SRI_CUDA(cudaFuncSetAttribute(sri::stage_tma_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::stage_tma_kernel<STAGE>, 32 * sri::kStageTmaWarps, smem));
+    if (h->tma_smem[STAGE] != smem) {  // the layout depends on which optional inputs are present
+        SRI_CUDA(cudaFuncSetAttribute(sri::stage_tma_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tma_occ[STAGE], sri::stage_tma_kernel<STAGE>, 32 * sri::kStageTmaWarps, smem));
+        h->tma_smem[STAGE] = smem;
+    }
+    const int occ = h->tma_occ[STAGE];
     if (occ < 1) return launch_stage_dmma<STAGE>(h, p);
     const long long want = (tiles + sri::kStageTmaWarps - 1) / sri::kStageTmaWarps;
     const long long cap = (long long)h->sm_count * occ;
