@@ -17,8 +17,9 @@
 // Measured alternatives to the plain barrier per step: owner look-ahead (-2..7 %) and a release/acquire
 // publication counter with a 16-slot ring instead of the barrier (-3 %; with the owner's sub-partition peers held back
 // until its critical DMMAs are issued +3 % at N = 64, -22 % at N = 32), the same with mbarrier try_wait instead of polling
-// (-10 %, -21 %), barrier + look-ahead + peers held back (-13 %).  bar.sync waits cost no issue slots and resume at once;
-// none of the finer-grained schemes recovered what they spend.
+// (-10 %, -21 %), barrier + look-ahead + peers held back (-13 %), barrier + early pivot element so that the reciprocal
+// chain hides behind the bulk DMMAs (-10 %).  bar.sync waits cost no issue slots and resume at once, and one instruction
+// stream shared by all warps beats every scheme that gives the owner its own.
 // Stages 2-4: [M x M] x [M x 3] DMMA contractions against fragment-ordered operator tables, one 8-row m-tile per warp,
 // boundary terms as the last k index.
 #pragma once
