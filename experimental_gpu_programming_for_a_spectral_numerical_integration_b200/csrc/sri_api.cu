@@ -839,12 +839,10 @@ int sri_create(int N, int device, sri_handle* out) {
         if (h->R == 32) {
             h->generic_smem = sri::TiledSmem<16, 4>::total() * sizeof(double);
             SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
-            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
             SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::tiled_kernel<16, 4, true>, 128, h->generic_smem));
         } else {
             h->generic_smem = sri::TiledSmem<32, 8>::total() * sizeof(double);
             SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<32, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
-            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<32, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
             SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::tiled_kernel<32, 8, true>, 256, h->generic_smem));
         }
         if (h->generic_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: generic kernel does not fit on this device"); }
