@@ -383,12 +383,17 @@ def test_high_resolution_node_counts(sri_lib, make_oracle, torch_mod, N, batch):
     q0 = rng.normal(size=(batch, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
     r0 = rng.normal(size=(batch, 3))
     lbar = rng.normal(size=(batch, 3, N))
+    Gamma = np.concatenate([1 + 0.1 * rng.normal(size=(batch, 1, N)), 0.1 * rng.normal(size=(batch, 2, N))], axis=1)
     ref = o.integrate_all(K, F, Mt, q0=q0, r0=r0, fbar=fb, lbar=lbar)
+    refG = o.integrate_all(K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fb, lbar=lbar)
     with SpectralRodIntegrator(N, 0) as h:
         got = _gpu_all(h, torch_mod, K, F, Mt, q0=q0, r0=r0, fbar=fb, lbar=lbar)
         assert (got["info"] == 0).all()
         for s in "Qrnm":
             assert rel_err(got[s], ref[s]) <= TOL, (N, s, rel_err(got[s], ref[s]))
+        gotG = _gpu_all(h, torch_mod, K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fb, lbar=lbar)  # shearable rod: nodal Gamma
+        for s in "Qrnm":
+            assert rel_err(gotG[s], refG[s]) <= TOL, (N, s, "Gamma", rel_err(gotG[s], refG[s]))
         # separate-stage entry points on the same handle
         t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
         Q = h.integrate_quaternions(t(K), q0=t(q0))
