@@ -18,6 +18,7 @@
 #include "sri_generic.cuh"
 #include "sri_stage_dmma.cuh"
 #include "sri_stage_generic.cuh"
+#include "sri_stage_generic_tma.cuh"
 #include "sri_stage_tma.cuh"
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
@@ -75,6 +76,8 @@ struct sri_context {
     bool use_dmma = false;
     size_t tma_smem[3] = {0, 0, 0};  // last shared-memory size configured per TMA stage kernel, and its occupancy
     int tma_occ[3] = {0, 0, 0};
+    size_t gtma_smem[3] = {0, 0, 0};  // the same for the 17 <= N <= 64 TMA stage kernels
+    int gtma_occ[3] = {0, 0, 0};
     int stage_impl = 0;          // N <= 16 separate-stage entry points: 0 = measured best per stage (position, couple: TMA-staged;
                                  // stress: direct loads), 1 = SRI_STAGE_IMPL=tma everywhere, 2 = SRI_STAGE_IMPL=ldg everywhere       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
     // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
@@ -592,6 +595,35 @@ int launch_stage_dmma(sri_context* h, const sri::FusedParams& p) {
     return SRI_OK;
 }
 
+// the rods [done, batch) of a separate-stage call
+sri::FusedParams stage_tail(const sri::FusedParams& p, long long done) {
+    const int M = p.M, N = p.N;
+    sri::FusedParams t = p;
+    t.batch = p.batch - done;
+    if (t.Qin) t.Qin += done * 4 * M;
+    if (t.nin) t.nin += done * 3 * M;
+    if (t.Gamma) t.Gamma += done * 3 * N;
+    if (t.fbar) t.fbar += done * 3 * N;
+    if (t.lbar) t.lbar += done * 3 * N;
+    if (t.F_tip) t.F_tip += done * 3;
+    if (t.M_tip) t.M_tip += done * 3;
+    if (t.q0) t.q0 += done * 4;
+    if (t.r0) t.r0 += done * 3;
+    if (t.r) t.r += done * 3 * M;
+    if (t.n) t.n += done * 3 * M;
+    if (t.m) t.m += done * 3 * M;
+    return t;
+}
+
+template <int STAGE>
+bool stage_pointers_aligned(const sri::FusedParams& p) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const double* load = (STAGE == sri::kStageStress) ? p.fbar : p.lbar;
+    const double* tip = (STAGE == sri::kStageStress) ? p.F_tip : p.M_tip;
+    double* out = (STAGE == sri::kStagePosition) ? p.r : (STAGE == sri::kStageStress ? p.n : p.m);
+    return al(p.Qin) && al(p.nin) && al(p.Gamma) && al(load) && al(tip) && al(p.q0) && al(p.r0) && al(out);
+}
+
 // Separate-stage entry points for N <= 16: whole tiles of 8 rods through the TMA-staged kernel when every pointer is
 // 16-byte aligned, the ragged tail (and unaligned calls) through the direct-load kernel.
 template <int STAGE>
@@ -600,11 +632,8 @@ int launch_stage(sri_context* h, const sri::FusedParams& p_in) {
     sri::FusedParams p = p_in;
     const int M = p.M, N = p.N;
     const long long tiles = p.batch / 8;
-    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const double* load = (STAGE == sri::kStageStress) ? p.fbar : p.lbar;
-    const double* tip = (STAGE == sri::kStageStress) ? p.F_tip : p.M_tip;
-    double* out = (STAGE == sri::kStagePosition) ? p.r : (STAGE == sri::kStageStress ? p.n : p.m);
-    const bool aligned = al(p.Qin) && al(p.nin) && al(p.Gamma) && al(load) && al(tip) && al(p.q0) && al(p.r0) && al(out);
+    const bool aligned = stage_pointers_aligned<STAGE>(p);
     // stress reads [3][16] stacks whose rows are 128-byte aligned: direct loads are already sector-exact there (92 % of HBM
     // against 83 % through shared memory); position / couple read 15-double rows and gain 5 % / 37 % from the staging
     const bool want_tma = h->stage_impl == 1 || (h->stage_impl == 0 && STAGE != sri::kStageStress);
@@ -635,33 +664,15 @@ int launch_stage(sri_context* h, const sri::FusedParams& p_in) {
     sri::stage_tma_kernel<STAGE><<<(int)(want < cap ? want : cap), 32 * sri::kStageTmaWarps, smem, h->stream>>>(p, L, tiles);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
-    const long long done = tiles * 8;
-    if (done < p.batch) {
-        sri::FusedParams t = p;
-        t.batch = p.batch - done;
-        if (t.Qin) t.Qin += done * 4 * M;
-        if (t.nin) t.nin += done * 3 * M;
-        if (t.Gamma) t.Gamma += done * 3 * N;
-        if (t.fbar) t.fbar += done * 3 * N;
-        if (t.lbar) t.lbar += done * 3 * N;
-        if (t.F_tip) t.F_tip += done * 3;
-        if (t.M_tip) t.M_tip += done * 3;
-        if (t.q0) t.q0 += done * 4;
-        if (t.r0) t.r0 += done * 3;
-        if (t.r) t.r += done * 3 * M;
-        if (t.n) t.n += done * 3 * M;
-        if (t.m) t.m += done * 3 * M;
-        return launch_stage_dmma<STAGE>(h, t);
-    }
+    if (tiles * 8 < p.batch) return launch_stage_dmma<STAGE>(h, stage_tail(p, tiles * 8));
     return SRI_OK;
 }
 
-// Separate-stage entry points for 17 <= N <= 64: streaming DMMA contraction against the fragment-ordered operator tables.
+// Separate-stage entry points for 17 <= N <= 64: streaming DMMA contraction against the fragment-ordered operator tables;
+// whole tiles of 8 rods with TMA-staged inputs when the pointers are 16-byte aligned, the rest with direct loads.
 template <int STAGE>
-int launch_stage_generic(sri_context* h, const sri::FusedParams& p_in) {
-    if (p_in.batch <= 0) return SRI_OK;
-    sri::FusedParams p = p_in;
-    p.ops2 = h->d_ops2;
+int launch_stage_generic_direct(sri_context* h, const sri::FusedParams& p) {
+    if (p.batch <= 0) return SRI_OK;
     const long long tiles = (p.batch + 7) / 8;
     const long long want = (tiles + 3) / 4;
     const size_t smem = (size_t)h->R * h->R * sizeof(double);
@@ -678,6 +689,58 @@ int launch_stage_generic(sri_context* h, const sri::FusedParams& p_in) {
     else sri::stage_generic_kernel<STAGE, 64><<<grid, 128, smem, h->stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+template <int STAGE>
+int launch_stage_generic(sri_context* h, const sri::FusedParams& p_in) {
+    if (p_in.batch <= 0) return SRI_OK;
+    sri::FusedParams p = p_in;
+    p.ops2 = h->d_ops2;
+    const int M = p.M, N = p.N;
+    const long long tiles = p.batch / 8;
+    // as for N <= 16: the force stage reads 128-byte aligned [3][N] rows and is faster with direct loads (N = 32: 72 % of HBM
+    // against 62 % staged), position and couple gain from the staging (N = 32: 64 -> 75 %, 59 -> 91 %; N = 64: +47 %, +20 %)
+    const bool want_tma = h->stage_impl == 1 || (h->stage_impl == 0 && STAGE != sri::kStageStress);
+    if (!want_tma || tiles == 0 || !stage_pointers_aligned<STAGE>(p)) return launch_stage_generic_direct<STAGE>(h, p);
+    const double* load = (STAGE == sri::kStageStress) ? p.fbar : p.lbar;
+    const double* tip = (STAGE == sri::kStagePosition) ? p.r0 : (STAGE == sri::kStageStress ? p.F_tip : p.M_tip);
+    sri::StageTmaLayout L{};
+    int off = 0;
+    auto put = [&](bool present, int bytes) { if (!present) return -1; const int o = off; off += bytes; return o; };
+    L.q = put(STAGE != sri::kStageStress, 8 * 4 * M * 8);
+    L.nin = put(STAGE == sri::kStageCouple, 8 * 3 * M * 8);
+    L.gam = put(STAGE != sri::kStageStress && p.Gamma, 8 * 3 * N * 8);
+    L.load = put(STAGE != sri::kStagePosition && load, 8 * 3 * N * 8);
+    L.tip = put(tip != nullptr, 192);
+    L.q0 = put(STAGE == sri::kStageCouple && p.q0, 256);
+    L.r0 = -1;
+    L.in_bytes = off;
+    L.out = 0;
+    L.warp_bytes = off;
+    if (off == 0) return launch_stage_generic_direct<STAGE>(h, p);  // nothing to stage (force stage without inputs)
+    const size_t smem = (size_t)h->R * h->R * sizeof(double) + (size_t)4 * off;
+    if (smem > 220 * 1024) return launch_stage_generic_direct<STAGE>(h, p);
+    if (h->gtma_smem[STAGE] != smem) {
+        if (h->R == 32) {
+            SRI_CUDA(cudaFuncSetAttribute(sri::stage_generic_tma_kernel<STAGE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->gtma_occ[STAGE], sri::stage_generic_tma_kernel<STAGE, 32>, 128, smem));
+        } else {
+            SRI_CUDA(cudaFuncSetAttribute(sri::stage_generic_tma_kernel<STAGE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->gtma_occ[STAGE], sri::stage_generic_tma_kernel<STAGE, 64>, 128, smem));
+        }
+        h->gtma_smem[STAGE] = smem;
+    }
+    const int occ = h->gtma_occ[STAGE];
+    if (occ < 1) return launch_stage_generic_direct<STAGE>(h, p);
+    const long long want = (tiles + 3) / 4;
+    const long long cap = (long long)h->sm_count * occ;
+    const int grid = (int)(want < cap ? want : cap);
+    if (h->R == 32) sri::stage_generic_tma_kernel<STAGE, 32><<<grid, 128, smem, h->stream>>>(p, L, tiles);
+    else sri::stage_generic_tma_kernel<STAGE, 64><<<grid, 128, smem, h->stream>>>(p, L, tiles);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    if (tiles * 8 < p.batch) return launch_stage_generic_direct<STAGE>(h, stage_tail(p, tiles * 8));
     return SRI_OK;
 }
 

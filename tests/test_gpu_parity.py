@@ -141,8 +141,9 @@ def test_stage_kernels_tma_and_direct(monkeypatch, sri_lib, make_oracle, torch_m
     assert rel_err(m2.cpu().numpy(), ref["m"][1:]) <= TOL
 
 
+@pytest.mark.parametrize("impl", ["default", "tma", "ldg"])
 @pytest.mark.parametrize("N,B", [(17, 130), (32, 257), (40, 33), (64, 101)])
-def test_high_resolution_stage_kernels(sri_lib, make_oracle, torch_mod, N, B):
+def test_high_resolution_stage_kernels(monkeypatch, sri_lib, make_oracle, torch_mod, N, B, impl):
     """Separate-stage entry points for 17 <= N <= 64 (streaming DMMA contraction, csrc/sri_stage_generic.cuh): every
     optional input, the no-load force stage, ragged tiles."""
     from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
@@ -156,7 +157,7 @@ def test_high_resolution_stage_kernels(sri_lib, make_oracle, torch_mod, N, B):
     ref = o.integrate_all(K, F, Mt, q0=q0, r0=r0, Gamma=Gamma, fbar=fb, lbar=lbar)
     ref0 = o.integrate_all(K, F, Mt)  # defaults: Gamma = e1, q0 = identity, no loads
     t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
-    with SpectralRodIntegrator(N, 0) as h:
+    with _handle_with_env(monkeypatch, N, SRI_STAGE_IMPL=impl) as h:  # TMA-staged / direct-load data paths
         Q = h.integrate_quaternions(t(K), q0=t(q0))
         r = h.integrate_position(Q, Gamma=t(Gamma), r0=t(r0))
         n = h.integrate_stress(t(F), fbar=t(fb))
