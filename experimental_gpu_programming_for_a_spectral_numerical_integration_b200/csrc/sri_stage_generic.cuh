@@ -17,7 +17,7 @@ namespace sri {
 
 template <int STAGE, int R>
 __global__ void __launch_bounds__(128) stage_generic_kernel(const FusedParams p) {
-    constexpr int KT = R / 4, MT = R / 8;
+    constexpr int KT = R / 4;
     extern __shared__ __align__(16) double gsm[];  // R*R doubles: AS (position) or AT (force, couple)
     const int lane = threadIdx.x & 31;
     const int lr = lane >> 2, lk = lane & 3;
