@@ -336,6 +336,34 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         cfg2 = {"workload": "cfg2: 10^4 rods, N=16, 1 GPU (a single 2.8-wave launch; L2-resident after the first pass)",
                 "rods_per_s": Bs / (e2.elapsed_time(e3) / 50 * 1e-3), "us_per_launch": e2.elapsed_time(e3) / 50 * 1e3}
 
+    # ---- BASELINE configs[3] (10^5 rods at N = 32 and N = 64), device-resident, beside the headline workload ---------
+    cfg4 = None
+    if world == 1:
+        cfg4 = {}
+        for Nh, flops in ((32, 1_320_063), (64, 10_869_012)):
+            Bh, Mh = 100_000, Nh - 1
+            hh = SpectralRodIntegrator(Nh, local_rank)
+            hh.set_stream(stream)
+            Kh = torch.empty((Bh, 3, Nh), dtype=f64, device=dev); Fh = torch.empty((Bh, 3), dtype=f64, device=dev)
+            Mh_t = torch.empty((Bh, 3), dtype=f64, device=dev); fbh = torch.empty((Bh, 3, Nh), dtype=f64, device=dev)
+            hh.generate_rods(SEED, 0, Bh, Kh, Fh, Mh_t, fbh)
+            outs = {k: torch.empty((Bh, c, Mh), dtype=f64, device=dev) for k, c in (("Q", 4), ("r", 3), ("n", 3), ("m", 3))}
+            run = lambda: hh.integrate_all(Kh, Fh, Mh_t, fbar=fbh, **outs)
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize(dev)
+            e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e4.record(stream)
+            for _ in range(3):
+                run()
+            e5.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e4.elapsed_time(e5) / 3
+            cfg4[f"N{Nh}"] = {"workload": f"cfg4: 10^5 rods, N={Nh}, 1 GPU, all 4 stages fused", "rods_per_s": Bh / (ms * 1e-3),
+                              "ms_per_launch": ms, "dense_count_tflops": Bh / (ms * 1e-3) * flops * 1e-12}
+            hh.close()
+            del Kh, Fh, Mh_t, fbh, outs
+
     if rank != 0:
         return
 
@@ -386,6 +414,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     }
     if cfg2 is not None:
         line["other_configs"] = {"cfg2": cfg2}
+        if cfg4:
+            line["other_configs"]["cfg4"] = cfg4
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     print(json.dumps(line), flush=True)
