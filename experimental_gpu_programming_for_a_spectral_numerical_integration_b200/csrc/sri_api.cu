@@ -537,15 +537,19 @@ int pipe_reserve(sri_context* h, int slot, int arr, size_t bytes, void** out) {
 int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
     const int N = h->N, M = h->M;
     const int64_t B = r->batch;
-    const int64_t chunk = (N <= 16) ? 32768 : (N <= 32 ? 8192 : 2048);
+    // chunk schedule: a short first chunk fills the pipeline quickly (its H2D copy and kernel are the only work that is
+    // not hidden behind the D2H stream, which bounds the call), the following ones are long enough that the per-transfer
+    // set-up of the copy engines does not show
+    const int64_t chunk = (N <= 16) ? 65536 : (N <= 32 ? 16384 : 4096);
+    const int64_t first_chunk = chunk / 8;
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl)
         if (!h->pipe_stream[sl]) SRI_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[sl], cudaStreamNonBlocking));
     struct Arr { const void* src; void* dst; size_t per_rod; };
     int c = 0;
-    for (int64_t first = 0; first < B; first += chunk, ++c) {
+    for (int64_t first = 0, step = first_chunk; first < B; first += step, step = chunk, ++c) {
         const int slot = c % sri_context::kPipeSlots;
         cudaStream_t st = h->pipe_stream[slot];
-        const int64_t nb = (B - first < chunk) ? (B - first) : chunk;
+        const int64_t nb = (B - first < step) ? (B - first) : step;
         const Arr ins[8] = {{r->K, nullptr, (size_t)3 * N * 8}, {r->q0, nullptr, 32}, {r->r0, nullptr, 24},
                             {r->Gamma, nullptr, (size_t)3 * N * 8}, {r->fbar, nullptr, (size_t)3 * N * 8},
                             {r->lbar, nullptr, (size_t)3 * N * 8}, {r->F_tip, nullptr, 24}, {r->M_tip, nullptr, 24}};

@@ -428,9 +428,9 @@ def test_cpp_dropin_reproduces_reference_main(sri_lib):
 
 
 def test_host_pipeline_multi_chunk_is_bit_identical_to_device_path(h16, oracle16, torch_mod):
-    """Host buffers larger than one pipeline chunk (32768 rods): chunked H2D/kernel/D2H must reproduce the
+    """Host buffers larger than the pipeline chunks (8192 rods, then 65536 each): chunked H2D/kernel/D2H must reproduce the
     device-resident call bit for bit, including the ragged last chunk."""
-    B = 2 * 32768 + 4097
+    B = 8192 + 65536 + 4097
     K, F, Mt, fb = oracle16.generate_rods(0x5EED, 10 ** 9, B)
     dev = _gpu_all(h16, torch_mod, K, F, Mt, fbar=fb)
     info = np.full(B, -1, dtype=np.int32)
