@@ -30,7 +30,7 @@ SEED = 0x5EED
 METRIC = "rod-integrations/sec (N=16, 4 stages, FP64)"
 # SURVEY 8(d) / BASELINE.md section 2: algorithmic work of one rod-integration, dense real formulation
 FLOPS_PER_ROD_DENSE = 155_700
-DMMA_PER_ROD = 223  # tensor-core instructions the fused kernel issues per rod (csrc/sri_fused16_dmma.cuh)
+DMMA_PER_ROD = 215  # tensor-core instructions the fused kernel issues per rod (csrc/sri_fused16_dmma.cuh)
 BYTES_PER_ROD = 1_992 + 3 * N_NODES * 8  # compulsory HBM traffic incl. the nodal fbar this workload supplies
 
 
@@ -398,8 +398,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                       "same system as a 15x15 quaternion system, which needs ~4x fewer flops, so frac may exceed 1; "
                       "`executed` is what the tensor pipe actually does",
         "executed": {"dmma_per_rod": DMMA_PER_ROD, "tflops": executed, "frac": executed / peak,
-                     "note": "223 DMMA m8n8k4 (512 flop each) per rod: 176 rank-4 updates, 23 pivot-row normalisations, "
-                             "24 stage contractions; dead columns and padding included"},
+                     "note": "215 DMMA m8n8k4 (512 flop each) per rod: 176 rank-4 updates, 23 pivot-row normalisations, "
+                             "16 stage contractions (position and force share one); dead columns and padding included"},
         "traffic": traffic,
         "hbm": {"achieved": BYTES_PER_ROD * B / (kernel_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": BYTES_PER_ROD * B / (kernel_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src,

@@ -55,7 +55,7 @@ constexpr int kDmmaTabDoubles = 768;  // Stx | AS | AT in shared memory
 struct DmmaScratch {
     static constexpr int kx = 0;                // [2][4][16] (double buffered): row 0 = (0,..,0,q0w), rows 1..3 = (K_c[0..M-1], 0.., q0_c)
     static constexpr int bs = kx + 128;         // [4][20] r' = R(q) Gamma at nodes 0..14 | r0
-    static constexpr int fbs = bs + 80;         // [4][20] fbar at nodes 1..15 (slot j = node j+1) | F_tip
+    static constexpr int fbs = bs + 80;         // [4][20] fbar at nodes 1..M in REVERSED order (slot j = node M-j) | F_tip
     static constexpr int xs = fbs + 80;         // [4][20] r' x n + lbar at nodes 1..15 | M_tip
     static constexpr int rps = xs + 80;         // [3][16] r' at all 16 nodes
     static constexpr int lbs = rps + 48;        // [3][16] lbar at nodes 1..15 (slot j = node j+1)
@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
     const int diag_code = (rr == 0) ? (4 * hi + cp) : -1;
     // B-fragment read offset into a [4][20] right-hand side
     const int offb = (rho < 3 ? rho : 3) * 20 + cp;
+    // stages 2+3 in one contraction: columns 0..2 = r' (bs), columns 3..5 = reversed fbar (fbs), the rest the zero row of bs
+    const int offb23 = (rho < 3 ? DmmaScratch::bs + rho * 20 : (rho < 6 ? DmmaScratch::fbs + (rho - 3) * 20 : DmmaScratch::bs + 60)) + cp;
 
     const long long stride = (long long)gridDim.x * kWarps;
     const long long rod0 = (long long)blockIdx.x * kWarps + warp;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
         if (row < N) {
             const int c0 = half ? 2 : 0, c1 = half ? 3 : 2;  // half 0: components 0, 1; half 1: component 2
             for (int c = c0; c < c1; ++c) {
-                if (p.fbar && row >= 1) cp_async8(scr + DmmaScratch::fbs + 20 * c + row - 1, p.fbar + (rod * 3 + c) * N + row);
+                if (p.fbar && row >= 1) cp_async8(scr + DmmaScratch::fbs + 20 * c + (M - row), p.fbar + (rod * 3 + c) * N + row);  // flipped, see stages 2+3
                 if (p.lbar && row >= 1) cp_async8(scr + DmmaScratch::lbs + 16 * c + row - 1, p.lbar + (rod * 3 + c) * N + row);
                 if (p.Gamma) cp_async8(scr + DmmaScratch::gam + 16 * c + row, p.Gamma + (rod * 3 + c) * N + row);
             }
@@ -345,24 +347,39 @@ __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma
             }
             __syncwarp();
             double acc[2][2];
-            if (p.r) {
-                // stage 2: r = Dn_NN^-1 (R(q) Gamma) + g r0^T
-                stage_dmma16<0>(tabAS, scr + DmmaScratch::bs + offb, lane, acc);
-                if (keep) store_stage(p.r + rod * 3 * M, M, rho, cp, acc);
+            // stages 2 and 3 in ONE contraction against Dn_NN^-1: the Chebyshev matrix is centro-antisymmetric, so
+            // -D_TT^-1 = J Dn_NN^-1 J (J = exchange matrix; 4e-16 on the as-built inverses) and gT = J g, hence
+            //   r      = S (R(q) Gamma)    + g r0^T        -> columns 0..2 of the B operand, rows in natural order
+            //   J n    = S (J fbar[1:])    + g F_tip^T     -> columns 3..5, right-hand side and result in reversed order
+            // C fragment: lane (rho, cp) holds row 8 mt + rho of columns 2cp, 2cp+1.
+            stage_dmma16<0>(tabAS, scr + offb23, lane, acc);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int i = 8 * mt + rho;
+                if (i < M && keep) {
+                    if (p.r) {
+                        double* d = p.r + rod * 3 * M + i;
+                        if (cp == 0) { d[0] = acc[mt][0]; d[M] = acc[mt][1]; }
+                        else if (cp == 1) d[2 * M] = acc[mt][0];
+                    }
+                    if (p.n) {
+                        double* d = p.n + rod * 3 * M + (M - 1 - i);
+                        if (cp == 1) d[0] = acc[mt][1];
+                        else if (cp == 2) { d[M] = acc[mt][0]; d[2 * M] = acc[mt][1]; }
+                    }
+                }
             }
             if (p.n || p.m) {
-                // stage 3: n = (-D_TT^-1) fbar[1:] + gT F_tip^T
-                if (p.fbar) stage_dmma16<0>(tabAT, scr + DmmaScratch::fbs + offb, lane, acc);
-                else stage_dmma16<3>(tabAT, scr + DmmaScratch::fbs + offb, lane, acc);
-                if (p.n && keep) store_stage(p.n + rod * 3 * M, M, rho, cp, acc);
                 if (p.m) {
                     // stage 4: m = (-D_TT^-1) (r' x n + lbar)[1:] + gT M_tip^T
                     double* nsv = scr + DmmaScratch::ns;
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         const int i = 8 * mt + rho;
-                        if (cp == 0) { nsv[i] = acc[mt][0]; nsv[16 + i] = acc[mt][1]; }
-                        else if (cp == 1) nsv[32 + i] = acc[mt][0];
+                        if (i < M) {
+                            if (cp == 1) nsv[M - 1 - i] = acc[mt][1];
+                            else if (cp == 2) { nsv[16 + M - 1 - i] = acc[mt][0]; nsv[32 + M - 1 - i] = acc[mt][1]; }
+                        }
                     }
                     __syncwarp();
                     if (half == 0 && row < 15) {
