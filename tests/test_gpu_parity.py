@@ -442,3 +442,42 @@ def test_host_pipeline_multi_chunk_is_bit_identical_to_device_path(h16, oracle16
     outp = h16.integrate_all(pinned["K"], pinned["F"], pinned["M"], fbar=pinned["fb"],
                              Q=torch_mod.empty((B, 4, 15), dtype=torch_mod.float64).pin_memory(), want=("Q", "m"))
     assert np.array_equal(outp["Q"].numpy(), dev["Q"]) and np.array_equal(outp["m"].numpy(), dev["m"])
+
+
+def test_full_size_batch_properties(h16, oracle16, torch_mod):
+    """BASELINE configs[2] at full size (10^6 rods, N = 16) through size-independent properties: no rod reported or handed
+    back, the exact force integral n(X) = F_tip + (1 - X) fbar for the constant distributed load of the workload, unit
+    quaternions up to the discretisation error, slices against the oracle, and bit-identity of a slice recomputed alone
+    (the sharding argument: a rod's result does not depend on which batch it travels in)."""
+    torch = torch_mod
+    B, N, M = 1_000_000, 16, 15
+    f64 = torch.float64
+    K = torch.empty((B, 3, N), dtype=f64, device="cuda"); F = torch.empty((B, 3), dtype=f64, device="cuda")
+    Mt = torch.empty((B, 3), dtype=f64, device="cuda"); fb = torch.empty((B, 3, N), dtype=f64, device="cuda")
+    h16.generate_rods(0x5EED, 0, B, K, F, Mt, fb)
+    info = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    out = h16.integrate_all(K, F, Mt, fbar=fb, info=info)
+    h16.synchronize()
+    assert int(info.abs().sum().item()) == 0 and h16.handback_count() == 0
+    for s_ in "Qrnm":
+        assert bool(torch.isfinite(out[s_]).all()), s_
+    # exact force integral (fbar is constant along each rod): nodes 1..15, X descending from the tip
+    x = torch.from_numpy(oracle16.chebyshev_points()).cuda()
+    n_exact = F[:, :, None] + fb[:, :, 1:] * (1.0 - x[None, None, 1:])
+    scale = n_exact.abs().amax(dim=(1, 2)).clamp_min(1e-300)
+    assert float(((out["n"] - n_exact).abs().amax(dim=(1, 2)) / scale).max().item()) <= 1e-12
+    # unit quaternions up to the spectral discretisation error (SURVEY T8; |K| <= 7 here)
+    qn = (out["Q"] ** 2).sum(dim=1).sqrt()
+    assert float((qn - 1).abs().max().item()) <= 1e-6
+    # slices against the oracle
+    for first in (0, 499_744, B - 512):
+        sl = slice(first, first + 512)
+        ref = oracle16.integrate_all(K[sl].cpu().numpy(), F[sl].cpu().numpy(), Mt[sl].cpu().numpy(), fbar=fb[sl].cpu().numpy())
+        for s_ in "Qrnm":
+            assert rel_err(out[s_][sl].cpu().numpy(), ref[s_]) <= TOL, (first, s_)
+    # a slice recomputed alone is bit-identical
+    sl = slice(700_001, 700_001 + 4099)
+    alone = h16.integrate_all(K[sl].contiguous(), F[sl].contiguous(), Mt[sl].contiguous(), fbar=fb[sl].contiguous())
+    h16.synchronize()
+    for s_ in "Qrnm":
+        assert torch.equal(alone[s_], out[s_][sl]), s_
