@@ -271,6 +271,20 @@ class SpectralRodIntegrator:
         )
         return out
 
+    def integrate_wrench_local(self, K, Q, F_tip, M_tip, q0=None, Gamma=None, fbar=None, lbar=None, out=None, info=None):
+        """Local-frame wrench [C; N] by a direct collocation solve of the local-frame statics (N <= 16), [batch][6][N]."""
+        self._follow_torch(K)
+        batch = K.shape[0]
+        if out is None:
+            out = _empty_like_kind(K, (batch, 6, self.N))
+        _lib.check(
+            self._lib.sri_integrate_wrench_local(self._h, batch, _ptr(K, "K"), _ptr(Q, "Q"), _ptr(q0, "q0"), _ptr(Gamma, "Gamma"),
+                                                 _ptr(fbar, "fbar"), _ptr(lbar, "lbar"), _ptr(F_tip, "F_tip"),
+                                                 _ptr(M_tip, "M_tip"), _ptr(out, "Lambda"), _ptr(info, "info", np.int32)),
+            "sri_integrate_wrench_local",
+        )
+        return out
+
     def project_onto_modes(self, f, ne: int, out=None):
         """Nodal field f [batch][3][N] -> modal coordinates [batch][3*ne] (Clenshaw-Curtis Galerkin projection)."""
         self._follow_torch(f)

@@ -22,6 +22,7 @@
 #include "sri_stage_tma.cuh"
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
+#include "sri_wrench_solve.cuh"
 
 // <row tiles per warp, column tiles, warps> of the N <= 32 instantiation of the multi-warp DMMA kernel
 #ifndef SRI_T32_RT
@@ -66,6 +67,7 @@ struct sri_context {
     size_t generic_smem = 0;
     int generic_blocks_per_sm = 0;
     double* d_ops2 = nullptr;    // N > 16: tables of the DMMA kernel (Stx | AS | AT, TiledDmmaCfg)
+    double* d_dtt = nullptr;     // D_TT (M x M, column-major) followed by D_TI (M): operator of the local-frame statics solve
     double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
@@ -920,6 +922,13 @@ int sri_create(int N, int device, sri_handle* out) {
         SRI_CUDA(cudaMalloc(&h->d_tnodes, sizeof(double) * N));
         SRI_CUDA(cudaMemcpy(h->d_tnodes, t.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
     }
+    {
+        std::vector<double> t((size_t)M * M + M);
+        std::copy(h->ops.D_TT.begin(), h->ops.D_TT.end(), t.begin());
+        std::copy(h->ops.D_TI.begin(), h->ops.D_TI.end(), t.begin() + (size_t)M * M);
+        SRI_CUDA(cudaMalloc(&h->d_dtt, sizeof(double) * t.size()));
+        SRI_CUDA(cudaMemcpy(h->d_dtt, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));
+    }
     SRI_CUDA(cudaMalloc(&h->d_reduce, sizeof(double) * 2));
     {
         std::vector<double> w(N);
@@ -960,6 +969,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_ops16) cudaFree(h->d_ops16);
     if (h->d_ops2) cudaFree(h->d_ops2);
     if (h->d_tnodes) cudaFree(h->d_tnodes);
+    if (h->d_dtt) cudaFree(h->d_dtt);
     if (h->d_reduce) cudaFree(h->d_reduce);
     if (h->d_ccw) cudaFree(h->d_ccw);
     for (int sl = 0; sl < 4; ++sl)
@@ -1178,6 +1188,40 @@ int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double*
     SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &dL));
     const long long total = (long long)batch * N;
     wrench_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, N, dQ, dq0, dn, dm, dF, dMt, dL);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, const double* Q, const double* q0,
+                               const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
+                               const double* M_tip, double* Lambda, int* info) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || (batch > 0 && (!K || !Q || !F_tip || !M_tip || !Lambda))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_wrench_local: bad arguments");
+    if (h->N > 16) return fail(SRI_ERR_UNSUPPORTED_N, "sri_integrate_wrench_local: N <= 16 (use sri_wrench_local on the global-frame stages for larger N)");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    Staging st(h);
+    sri::WrenchParams p{};
+    p.batch = batch; p.N = N; p.M = M; p.D_TT = h->d_dtt; p.D_TI = h->d_dtt + (size_t)M * M;
+    SRI_TRY(st.in(K, (size_t)batch * 3 * N, &p.K));
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &p.Q));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &p.q0));
+    SRI_TRY(st.in(Gamma, (size_t)batch * 3 * N, &p.Gamma));
+    SRI_TRY(st.in(fbar, (size_t)batch * 3 * N, &p.fbar));
+    SRI_TRY(st.in(lbar, (size_t)batch * 3 * N, &p.lbar));
+    SRI_TRY(st.in(F_tip, (size_t)batch * 3, &p.F_tip));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
+    SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &p.Lambda));
+    SRI_TRY(st.out(info, (size_t)batch, &p.info));
+    static bool configured = false;
+    if (!configured) {
+        SRI_CUDA(cudaFuncSetAttribute(sri::wrench_local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sri::kWrenchSmem));
+        configured = true;
+    }
+    const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
+    const long long cap = (long long)h->sm_count * 2;
+    sri::wrench_local_solve_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchWarps, sri::kWrenchSmem, h->stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();

@@ -144,6 +144,16 @@ int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const doubl
 int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* n, const double* m,
                      const double* F_tip, const double* M_tip, double* Lambda);
 
+/* The same wrench obtained by SOLVING the local-frame statics (rod_modeling.pdf eqs. 1.29, 2.18):
+ *   N' = -K^ N - R^T fbar,  C' = -K^ C - Gamma^ N - R^T lbar,  N(1) = R(1)^T F_tip,  C(1) = R(1)^T M_tip,
+ * collocated with the tip node eliminated: the strain-dependent operator D_TT (x) I3 + blockdiag(K^_i) (3M x 3M), one
+ * partial-pivot LU per rod and two solves.  Agrees with sri_wrench_local on the global-frame stages to the
+ * discretisation error (1e-8 at N = 16).  N <= 16.  K [batch][3][N]; Q [batch][4][M] from stage 1; optional inputs as
+ * in sri_integrate_all; Lambda [batch][6][N], couple first; info [batch] or NULL (zero-pivot step of the LU). */
+int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, const double* Q, const double* q0,
+                               const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
+                               const double* M_tip, double* Lambda, int* info);
+
 /* Galerkin projection of a nodal field onto the Legendre strain modes (rod_modeling.pdf eqs. 2.14, 2.16; the
  * transpose of Phi, include/utilities.h:49-67): out[b][c*ne+k] = sum_i w_i P_k(2 x_i - 1) f[b][c][i], with w the
  * Clenshaw-Curtis weights of the N Chebyshev nodes on [0,1].  f [batch][3][N] -> out [batch][3*ne]. */

@@ -77,6 +77,8 @@ class Oracle:
         L.sri_oracle_integrate_all_batch.argtypes = [c_int, c_long] + [c_void_p] * 12 + [c_int, c_int]
         L.sri_oracle_shape_residual.argtypes = [c_void_p] * 9
         L.sri_oracle_wrench_local.argtypes = [c_void_p] * 8
+        L.sri_oracle_wrench_local_solve.restype = c_int
+        L.sri_oracle_wrench_local_solve.argtypes = [c_void_p] * 10
         L.sri_oracle_max_threads.restype = c_int
         L.sri_oracle_generate_rods.argtypes = [c_int, ctypes.c_uint64, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p]
         self._ops = L.sri_oracle_ops_create(self.N)
@@ -175,6 +177,20 @@ class Oracle:
         for b in range(B):
             self.lib.sri_oracle_wrench_local(self._ops, _p(cz(Q[b])), None if q0 is None else _p(cz(q0[b])), _p(cz(n[b])),
                                              _p(cz(m[b])), _p(cz(F_tip[b])), _p(cz(M_tip[b])), lam[b].ctypes.data)
+        return lam
+
+    def wrench_local_solve(self, K, Q, F_tip, M_tip, q0=None, Gamma=None, fbar=None, lbar=None) -> np.ndarray:
+        """Local-frame statics solved directly (strain-dependent collocation operator): Lambda [B][6][N], couple first."""
+        B = K.shape[0]
+        lam = np.empty((B, 6, self.N))
+        cz = lambda a, b: None if a is None else _p(np.ascontiguousarray(a[b], dtype=np.float64))
+        keep = []
+        for b in range(B):
+            args = [np.ascontiguousarray(x[b], dtype=np.float64) if x is not None else None
+                    for x in (K, Q, q0, Gamma, fbar, lbar, F_tip, M_tip)]
+            keep.append(args)
+            bad = self.lib.sri_oracle_wrench_local_solve(self._ops, *[None if a is None else _p(a) for a in args], lam[b].ctypes.data)
+            assert bad == 0
         return lam
 
     def generate_rods(self, seed: int, first_rod: int, batch: int):

@@ -450,6 +450,71 @@ void sri_oracle_wrench_local(const sri_oracle_ops* o, const double* Q, const dou
     }
 }
 
+/* Local-frame statics solved directly (rod_modeling.pdf eqs. 1.29, 2.18, collocated as Ch. 3):
+ *   N' = -K^ N - R^T fbar,   C' = -K^ C - Gamma^ N - R^T lbar,   N(1) = R(1)^T F_tip,  C(1) = R(1)^T M_tip
+ * i.e. the strain-dependent operator (D_TT (x) I3 + blockdiag K^_i) over the nodes 1..N-1 with the tip node eliminated,
+ * one partial-pivot LU, two solves.  Lambda is [6][N], couple first (the [k; gamma] ordering of ad(), utilities.h:27-37).
+ * Returns 0, or k+1 if the LU met a zero pivot. */
+int sri_oracle_wrench_local_solve(const sri_oracle_ops* o, const double* K, const double* Q, const double* q0,
+                                  const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
+                                  const double* M_tip, double* Lambda)
+{
+    const int N = o->N, M = o->M, n = 3 * M;
+    static const double q_default[4] = {1.0, 0.0, 0.0, 0.0};
+    if (!q0) q0 = q_default;
+    double* A = (double*)calloc((size_t)n * n, sizeof(double));
+    double* R = (double*)malloc(sizeof(double) * 9 * N);
+    double* b = (double*)malloc(sizeof(double) * n);
+    int* piv = (int*)malloc(sizeof(int) * n);
+    for (int i = 0; i < N; ++i) {
+        if (i < M) quat_to_rot(Q[i], Q[i + M], Q[i + 2 * M], Q[i + 3 * M], R + 9 * i);
+        else quat_to_rot(q0[0], q0[1], q0[2], q0[3], R + 9 * i);
+    }
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < M; ++i)
+            for (int a = 0; a < 3; ++a) A[IDX(3 * i + a, 3 * j + a, n)] = o->D_TT[IDX(i, j, M)];
+    for (int i = 0; i < M; ++i) {
+        const double k0 = K[i + 1], k1 = K[N + i + 1], k2 = K[2 * N + i + 1];  /* node i+1 */
+        A[IDX(3 * i + 0, 3 * i + 1, n)] += -k2; A[IDX(3 * i + 0, 3 * i + 2, n)] += k1;
+        A[IDX(3 * i + 1, 3 * i + 0, n)] += k2;  A[IDX(3 * i + 1, 3 * i + 2, n)] += -k0;
+        A[IDX(3 * i + 2, 3 * i + 0, n)] += -k1; A[IDX(3 * i + 2, 3 * i + 1, n)] += k0;
+    }
+    const int info = lu_factor(n, A, piv);
+    double N0[3], C0[3];
+    for (int c = 0; c < 3; ++c) {
+        N0[c] = R[0 * 3 + c] * F_tip[0] + R[1 * 3 + c] * F_tip[1] + R[2 * 3 + c] * F_tip[2];
+        C0[c] = R[0 * 3 + c] * M_tip[0] + R[1 * 3 + c] * M_tip[1] + R[2 * 3 + c] * M_tip[2];
+    }
+    for (int i = 0; i < M; ++i) {
+        const double* Ri = R + 9 * (i + 1);
+        for (int c = 0; c < 3; ++c) {
+            double rf = 0.0;
+            if (fbar) rf = Ri[0 * 3 + c] * fbar[i + 1] + Ri[1 * 3 + c] * fbar[N + i + 1] + Ri[2 * 3 + c] * fbar[2 * N + i + 1];
+            b[3 * i + c] = -rf - o->D_TI[i] * N0[c];
+        }
+    }
+    lu_solve(n, A, piv, b, 1);
+    for (int c = 0; c < 3; ++c) { Lambda[(3 + c) * N] = N0[c]; Lambda[c * N] = C0[c]; }
+    for (int i = 0; i < M; ++i)
+        for (int c = 0; c < 3; ++c) Lambda[(3 + c) * N + i + 1] = b[3 * i + c];
+    for (int i = 0; i < M; ++i) {
+        const double* Ri = R + 9 * (i + 1);
+        const double g0 = Gamma ? Gamma[i + 1] : 1.0, g1 = Gamma ? Gamma[N + i + 1] : 0.0, g2 = Gamma ? Gamma[2 * N + i + 1] : 0.0;
+        const double n0 = Lambda[3 * N + i + 1], n1 = Lambda[4 * N + i + 1], n2 = Lambda[5 * N + i + 1];
+        const double gx[3] = {g1 * n2 - g2 * n1, g2 * n0 - g0 * n2, g0 * n1 - g1 * n0};
+        for (int c = 0; c < 3; ++c) {
+            double rl = 0.0;
+            if (lbar) rl = Ri[0 * 3 + c] * lbar[i + 1] + Ri[1 * 3 + c] * lbar[N + i + 1] + Ri[2 * 3 + c] * lbar[2 * N + i + 1];
+            b[3 * i + c] = -gx[c] - rl - o->D_TI[i] * C0[c];
+        }
+    }
+    lu_solve(n, A, piv, b, 1);
+    for (int i = 0; i < M; ++i)
+        for (int c = 0; c < 3; ++c) Lambda[c * N + i + 1] = b[3 * i + c];
+    free(A); free(R); free(b); free(piv);
+    return info;
+}
+
 /* ---- batched driver (OpenMP over rods) ----------------------------------------------------------------- */
 
 /* All four stages for `batch` rods.  Layouts match include/sri.h: K,Gamma,fbar,lbar [batch][3][N];

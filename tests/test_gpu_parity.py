@@ -358,6 +358,38 @@ def test_wrench_local_frame(h16, oracle16, torch_mod):
     assert np.abs(lam0[:, 3:, 1:] - out["n"]).max() <= 1e-13 and np.abs(lam0[:, :3, 1:] - out["m"]).max() <= 1e-13
 
 
+@pytest.mark.parametrize("N", [16, 9])
+def test_local_frame_statics_direct_solve(sri_lib, make_oracle, torch_mod, N):
+    """the local-frame statics solved directly on the GPU (strain-dependent 3M x 3M operator, warp-level
+    partial-pivot LU) against the oracle's restatement, and against the pointwise form of the global-frame stages (equal to
+    the discretisation error only)."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    o = make_oracle(N)
+    rng = np.random.default_rng(50 + N)
+    B = 203
+    x = o.chebyshev_points()
+    K, F, Mt, fb = o.generate_rods(0x5EED, 300, B)
+    fbar = fb + 0.3 * rng.normal(size=(B, 3, 1)) * np.sin(2 * x)[None, None, :]
+    lbar = 0.2 * rng.normal(size=(B, 3, 1)) * np.cos(x)[None, None, :]
+    Gamma = np.stack([1 + 0.05 * np.sin(x), 0.03 * x, 0.02 * np.cos(x)])[None].repeat(B, axis=0)
+    q0 = rng.normal(size=(B, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    ref = o.integrate_all(K, F, Mt, q0=q0, Gamma=Gamma, fbar=fbar, lbar=lbar)
+    lam_ref = o.wrench_local_solve(K, ref["Q"], F, Mt, q0=q0, Gamma=Gamma, fbar=fbar, lbar=lbar)
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    with SpectralRodIntegrator(N, 0) as h:
+        info = torch_mod.full((B,), -1, dtype=torch_mod.int32, device="cuda")
+        lam = h.integrate_wrench_local(t(K), t(ref["Q"]), t(F), t(Mt), q0=t(q0), Gamma=t(Gamma), fbar=t(fbar), lbar=t(lbar), info=info)
+        lam_pw = h.wrench_local(t(ref["Q"]), t(ref["n"]), t(ref["m"]), t(F), t(Mt), q0=t(q0))
+        # defaults (no optional input), host buffers
+        ref0 = o.integrate_all(K[:5], F[:5], Mt[:5])
+        lam0 = h.integrate_wrench_local(K[:5], ref0["Q"], F[:5], Mt[:5])
+        h.synchronize()
+    assert (info.cpu().numpy() == 0).all()
+    assert rel_err(lam.cpu().numpy(), lam_ref) <= TOL
+    assert rel_err(lam.cpu().numpy(), lam_pw.cpu().numpy()) <= (1e-6 if N == 16 else 1e-2)
+    assert rel_err(lam0, o.wrench_local_solve(K[:5], ref0["Q"], F[:5], Mt[:5])) <= TOL
+
+
 def test_shape_residual(h16, oracle16, torch_mod):
     B = 400
     K, F, Mt, fb = oracle16.generate_rods(21, 0, B)

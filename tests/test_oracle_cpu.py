@@ -258,6 +258,47 @@ def test_T10_global_vs_local_frame_statics(make_oracle, N, tol):
         assert np.abs(lam[b][3:, 0] - N0).max() <= 1e-15 and np.abs(lam[b][:3, 0] - C0).max() <= 1e-15
 
 
+@pytest.mark.parametrize("N,tol", [(16, 1e-7), (32, 1e-12)])
+def test_wrench_local_solve_vs_pointwise_and_numpy(make_oracle, N, tol):
+    """The oracle's direct local-frame solve (one LU of the strain-dependent operator, two solves) against (a) the
+    pointwise form [R^T m; R^T n] of the global-frame stages -- equal to discretisation error -- and (b) numpy/LAPACK on
+    the same collocation system -- equal to rounding."""
+    o = make_oracle(N)
+    M = N - 1
+    rng = np.random.default_rng(7 * N)
+    x = o.chebyshev_points()
+    K, F, Mt, fb = o.generate_rods(0x5EED, 11, 3)
+    fbar = fb + 0.3 * rng.normal(size=(3, 3, 1)) * np.sin(2 * x)[None, None, :]
+    lbar = 0.2 * rng.normal(size=(3, 3, 1)) * np.cos(x)[None, None, :]
+    Gamma = np.stack([1 + 0.05 * np.sin(x), 0.03 * x, 0.02 * np.cos(x)])[None].repeat(3, axis=0)
+    q0 = rng.normal(size=(3, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    out = o.integrate_all(K, F, Mt, q0=q0, Gamma=Gamma, fbar=fbar, lbar=lbar)
+    lam_pw = o.wrench_local(out["Q"], out["n"], out["m"], F, Mt, q0=q0)
+    lam = o.wrench_local_solve(K, out["Q"], F, Mt, q0=q0, Gamma=Gamma, fbar=fbar, lbar=lbar)
+    scale = np.abs(lam_pw).max()
+    assert np.abs(lam - lam_pw).max() <= tol * scale
+    # numpy on the same system
+    Dn = o.operator(0); D_TT, D_TI = Dn[1:, 1:], Dn[1:, 0]
+    skew = lambda v: np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+    def rot(q):
+        w, a, b, c = q
+        return np.array([[1 - 2 * (b * b + c * c), 2 * (a * b - w * c), 2 * (a * c + w * b)],
+                         [2 * (a * b + w * c), 1 - 2 * (a * a + c * c), 2 * (b * c - w * a)],
+                         [2 * (a * c - w * b), 2 * (b * c + w * a), 1 - 2 * (a * a + b * b)]])
+
+    for b in range(3):
+        R = [rot(out["Q"][b][:, i]) if i < M else rot(q0[b]) for i in range(N)]
+        A = np.kron(D_TT, np.eye(3))
+        for i in range(1, N):
+            A[3 * (i - 1):3 * i, 3 * (i - 1):3 * i] += skew(K[b][:, i])
+        N0, C0 = R[0].T @ F[b], R[0].T @ Mt[b]
+        Nl = np.linalg.solve(A, np.concatenate([-R[i].T @ fbar[b][:, i] for i in range(1, N)]) - np.kron(D_TI, N0)).reshape(M, 3)
+        rhs = np.concatenate([-np.cross(Gamma[b][:, i], Nl[i - 1]) - R[i].T @ lbar[b][:, i] for i in range(1, N)]) - np.kron(D_TI, C0)
+        Cl = np.linalg.solve(A, rhs).reshape(M, 3)
+        assert np.abs(lam[b][3:, 1:].T - Nl).max() <= 1e-12 * scale and np.abs(lam[b][:3, 1:].T - Cl).max() <= 1e-12 * scale
+
+
 # ---- independent restatements -----------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("N", [8, 16, 32])
