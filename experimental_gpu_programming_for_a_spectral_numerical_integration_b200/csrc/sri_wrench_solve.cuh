@@ -129,7 +129,16 @@ __global__ void __launch_bounds__(32 * kWrenchWarps) wrench_local_solve_kernel(c
                 const int c = c0 + lane;
                 if (c < n) {
                     const double u = A[k * LD + c];
-                    for (int r = k + 1; r < n; ++r) A[r * LD + c] -= A[r * LD + k] * u;
+                    int r = k + 1;
+                    // four rows at a time, loads before stores: the rows are independent, but the compiler cannot prove
+                    // that the store of one row does not alias the loads of the next (the plain loop ran 4 x slower)
+                    for (; r + 3 < n; r += 4) {
+                        double* a0 = A + r * LD;
+                        const double l0 = a0[k], l1 = a0[LD + k], l2 = a0[2 * LD + k], l3 = a0[3 * LD + k];
+                        const double v0 = a0[c], v1 = a0[LD + c], v2 = a0[2 * LD + c], v3 = a0[3 * LD + c];
+                        a0[c] = v0 - l0 * u; a0[LD + c] = v1 - l1 * u; a0[2 * LD + c] = v2 - l2 * u; a0[3 * LD + c] = v3 - l3 * u;
+                    }
+                    for (; r < n; ++r) A[r * LD + c] -= A[r * LD + k] * u;
                 }
             }
             __syncwarp();
