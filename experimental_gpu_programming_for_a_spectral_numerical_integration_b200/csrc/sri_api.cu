@@ -76,6 +76,7 @@ struct sri_context {
     int dmma_blocks_per_sm = 0;
     double dmma_growth = sri::kDmmaGrowthDefault;
     bool use_dmma = false;
+    bool wrench_configured = false;
     size_t tma_smem[3] = {0, 0, 0};  // last shared-memory size configured per TMA stage kernel, and its occupancy
     int tma_occ[3] = {0, 0, 0};
     size_t gtma_smem[3] = {0, 0, 0};  // the same for the 17 <= N <= 64 TMA stage kernels
@@ -1214,13 +1215,12 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &p.Lambda));
     SRI_TRY(st.out(info, (size_t)batch, &p.info));
-    static bool configured = false;
-    if (!configured) {
+    if (!h->wrench_configured) {
         SRI_CUDA(cudaFuncSetAttribute(sri::wrench_local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sri::kWrenchSmem));
-        configured = true;
+        h->wrench_configured = true;
     }
     const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
-    const long long cap = (long long)h->sm_count * 2;
+    const long long cap = (long long)h->sm_count;  // one CTA of 8 warps per SM (24 KB of shared memory per rod)
     sri::wrench_local_solve_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchWarps, sri::kWrenchSmem, h->stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
