@@ -30,7 +30,7 @@ namespace sri {
 constexpr int kWrenchWarps = 8;               // one CTA per SM
 constexpr int kWrenchNP = 48;                 // 3 (N - 1) rounded up to whole 8 x 8 tiles, N <= 16
 constexpr int kWrenchLD = 56;                 // doubles per row: 48 columns, the row-index column, padding
-constexpr int kWrenchShared = 256;            // D_TT [15][15] + D_TI [15], shared by the CTA's warps
+constexpr int kWrenchShared = 16 + kWrenchNP * kWrenchLD;  // D_TI [15]; the strain-independent part of A, shared by the warps
 struct WrenchScratch {                        // per warp, doubles
     static constexpr int A = 0;                              // [48][56]
     static constexpr int b = A + kWrenchNP * kWrenchLD;      // [48] right-hand side / solution
@@ -65,8 +65,8 @@ __device__ __forceinline__ void quat_to_rot_rm(const quat& q, double* R) {  // E
 
 __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kernel(const WrenchParams p) {
     extern __shared__ __align__(16) double wsm[];
-    double* dtt = wsm;          // [15][15] column-major
-    double* dti = wsm + 225;    // [15]
+    double* dti = wsm;          // [15]
+    double* tmpl = wsm + 16;    // [48][56]: D_TT (x) I3, identity on the padding rows, row index in column 48
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lr = lane >> 2, lk = lane & 3;
     double* scr = wsm + kWrenchShared + warp * WrenchScratch::total;
@@ -82,7 +82,14 @@ __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kerne
     constexpr unsigned FULL = 0xffffffffu;
     const int row1 = lane + 32;
     const bool has0 = lane < NP, has1 = row1 < NP;           // the rows this lane owns
-    for (int i = threadIdx.x; i < M * M; i += blockDim.x) dtt[i] = p.D_TT[i];
+    for (int e = threadIdx.x; e < kWrenchNP * LD; e += blockDim.x) {
+        const int r = e / LD, c = e - r * LD;
+        double v = 0.0;
+        if (r < n && c < n) { const int i = r / 3, j = c / 3; if (r - 3 * i == c - 3 * j) v = p.D_TT[j * M + i]; }
+        else if (c == 48) v = (double)r;
+        else if (r == c) v = 1.0;
+        tmpl[e] = v;
+    }
     for (int i = threadIdx.x; i < M; i += blockDim.x) dti[i] = p.D_TI[i];
     __syncthreads();
 
@@ -174,25 +181,14 @@ __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kerne
             quat_to_rot_rm(q, Rm + 9 * lane);
         }
         __syncwarp();
-        // ---- operator: lanes own columns; rows/columns n..NP-1 are an identity block, column 48 the row index --------
-        for (int r = 0; r < NP; ++r) {
-            const int i = r / 3, a = r - 3 * i;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int c = lane + 32 * s;
-                if (c < NP) {
-                    double v = 0.0;
-                    if (r < n && c < n) {
-                        const int j = c / 3, bb = c - 3 * j;
-                        if (a == bb) v = dtt[j * M + i];
-                        else if (i == j) {  // K^ of node i+1: [[0,-k2,k1],[k2,0,-k0],[-k1,k0,0]]
-                            const double kv = kk[(3 - a - bb) * N + i + 1];
-                            v = (bb == a + 2 || a == bb + 1) ? kv : -kv;
-                        }
-                    } else if (r == c) v = 1.0;
-                    A[r * LD + c] = v;
-                } else if (c == 48) A[r * LD + 48] = (double)r;
-            }
+        // ---- operator: the CTA's template plus this rod's 6 M off-diagonal entries of blockdiag(K^) -----------------
+        for (int e = lane; e < NP * (LD / 2); e += 32) reinterpret_cast<double2*>(A)[e] = reinterpret_cast<const double2*>(tmpl)[e];
+        __syncwarp();
+        for (int e = lane; e < 6 * M; e += 32) {  // K^ of node i+1: [[0,-k2,k1],[k2,0,-k0],[-k1,k0,0]]
+            const int i = e / 6, k = e - 6 * i;
+            const int a = k >> 1, bb = (a + 1 + (k & 1)) % 3;   // the two off-diagonal columns of row a
+            const double kv = kk[(3 - a - bb) * N + i + 1];
+            A[(3 * i + a) * LD + 3 * i + bb] = (bb == a + 2 || a == bb + 1) ? kv : -kv;
         }
         __syncwarp();
         // ---- blocked partial-pivot LU, in place ------------------------------------------------------------------------
