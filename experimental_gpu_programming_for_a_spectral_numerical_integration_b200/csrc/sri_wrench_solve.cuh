@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kerne
                     if (lane == (bi & 31)) { if (from1) act1 = false; else act0 = false; }
                     const bool singular = (mh | ml) == 0u || mh >= 0x7ff00000u;
                     if (singular && !bad && c0 + j < n) bad = c0 + j + 1;
-                    const double rp = 1.0 / pv[j][j];
+                    const double rp = __drcp_rn(pv[j][j]);
                     const double inv = singular ? 0.0 : rp;
                     if (lane == 0) dinv[c0 + j] = rp;
                     if (act0) {
@@ -266,30 +266,49 @@ __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kerne
             if (c0 < 16) panel(std::true_type{}); else panel(std::false_type{});
             __syncwarp();
             // ---- the exchanges that bring pivot row j to position c0 + j, whole rows (factors to the left, panel, trailing
-            //      block, row-index column), the lanes owning columns; then U12 = L11^-1 A12 in the same lane -------------
-            int q[4];
+            //      block, row-index column), the lanes owning columns; U12 = L11^-1 A12 on the way.  Written as one gather
+            //      (all loads, then all stores) of the arrangement that the sequence of exchanges j <-> q[j] produces:
+            //      position c0 + j receives pivot row j, a displaced row c0 + j that is no pivot goes to dest[j] ---------------
+            int dest[4];
+            bool disp[4], moved = false;
+            {
+                int q[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // where pivot row j sits after the exchanges 0..j-1
-                int t = pr[j];
+                for (int j = 0; j < 4; ++j) {  // where pivot row j sits after the exchanges 0..j-1
+                    int t = pr[j];
 #pragma unroll
-                for (int jp = 0; jp < j; ++jp) if (t == c0 + jp) t = q[jp];
-                q[j] = t;
+                    for (int jp = 0; jp < j; ++jp) if (t == c0 + jp) t = q[jp];
+                    q[j] = t;
+                    moved = moved || pr[j] != c0 + j;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    disp[j] = pr[0] != c0 + j && pr[1] != c0 + j && pr[2] != c0 + j && pr[3] != c0 + j;
+                    int t = c0 + j;
+#pragma unroll
+                    for (int jj = j; jj < 4; ++jj) if (t == c0 + jj) t = q[jj];
+                    dest[j] = t;
+                }
             }
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int c = lane + 32 * s;
-                if (c < NP || c == 48) {
+                const bool trailing = c >= c0 + 4 && c < NP;
+                if ((c < NP || c == 48) && (moved || trailing)) {
+                    double u[4], d[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (q[j] != c0 + j) { const double t = A[(c0 + j) * LD + c]; A[(c0 + j) * LD + c] = A[q[j] * LD + c]; A[q[j] * LD + c] = t; }
-                    if (c >= c0 + 4 && c < NP) {
-                        double* u = A + c0 * LD + c;
-                        const double u0 = u[0];
-                        const double u1 = fma(-pv[1][0], u0, u[LD]);
-                        const double u2 = fma(-pv[2][1], u1, fma(-pv[2][0], u0, u[2 * LD]));
-                        const double u3 = fma(-pv[3][2], u2, fma(-pv[3][1], u1, fma(-pv[3][0], u0, u[3 * LD])));
-                        u[LD] = u1; u[2 * LD] = u2; u[3 * LD] = u3;
+                    for (int j = 0; j < 4; ++j) u[j] = A[pr[j] * LD + c];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (disp[j]) d[j] = A[(c0 + j) * LD + c];
+                    if (trailing) {
+                        u[1] = fma(-pv[1][0], u[0], u[1]);
+                        u[2] = fma(-pv[2][1], u[1], fma(-pv[2][0], u[0], u[2]));
+                        u[3] = fma(-pv[3][2], u[2], fma(-pv[3][1], u[1], fma(-pv[3][0], u[0], u[3])));
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) A[(c0 + j) * LD + c] = u[j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (disp[j]) A[dest[j] * LD + c] = d[j];
                 }
             }
             __syncwarp();

@@ -358,7 +358,7 @@ def test_wrench_local_frame(h16, oracle16, torch_mod):
     assert np.abs(lam0[:, 3:, 1:] - out["n"]).max() <= 1e-13 and np.abs(lam0[:, :3, 1:] - out["m"]).max() <= 1e-13
 
 
-@pytest.mark.parametrize("N", [16, 9])
+@pytest.mark.parametrize("N", [16, 12, 9, 5])
 def test_local_frame_statics_direct_solve(sri_lib, make_oracle, torch_mod, N):
     """the local-frame statics solved directly on the GPU (strain-dependent 3M x 3M operator, warp-level
     partial-pivot LU) against the oracle's restatement, and against the pointwise form of the global-frame stages (equal to
@@ -386,8 +386,32 @@ def test_local_frame_statics_direct_solve(sri_lib, make_oracle, torch_mod, N):
         h.synchronize()
     assert (info.cpu().numpy() == 0).all()
     assert rel_err(lam.cpu().numpy(), lam_ref) <= TOL
-    assert rel_err(lam.cpu().numpy(), lam_pw.cpu().numpy()) <= (1e-6 if N == 16 else 1e-2)
+    if N >= 9:  # (5 nodes do not resolve these fields: the two forms then differ by tens of percent)
+        assert rel_err(lam.cpu().numpy(), lam_pw.cpu().numpy()) <= {16: 1e-6, 12: 1e-4, 9: 1e-2}[N]
     assert rel_err(lam0, o.wrench_local_solve(K[:5], ref0["Q"], F[:5], Mt[:5])) <= TOL
+
+
+def test_local_frame_statics_non_finite_rod_is_reported(sri_lib, make_oracle, torch_mod):
+    """A rod with NaN / Inf curvature samples is flagged through info[] (non-finite pivot) and leaves its neighbours alone."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    N, B = 16, 64
+    o = make_oracle(N)
+    K, F, Mt, fb = o.generate_rods(0x5EED, 4321, B)
+    ref = o.integrate_all(K, F, Mt, fbar=fb)
+    lam_ref = o.wrench_local_solve(K, ref["Q"], F, Mt, fbar=fb)
+    Kbad = K.copy()
+    Kbad[7, 1, 3] = np.nan
+    Kbad[40, 2, 9] = np.inf
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    with SpectralRodIntegrator(N, 0) as h:
+        info = torch_mod.full((B,), -1, dtype=torch_mod.int32, device="cuda")
+        lam = h.integrate_wrench_local(t(Kbad), t(ref["Q"]), t(F), t(Mt), fbar=t(fb), info=info)
+        h.synchronize()
+    info = info.cpu().numpy(); lam = lam.cpu().numpy()
+    good = np.setdiff1d(np.arange(B), [7, 40])
+    assert (info[good] == 0).all() and rel_err(lam[good], lam_ref[good]) <= TOL
+    for b in (7, 40):
+        assert info[b] != 0 or not np.isfinite(lam[b]).all()
 
 
 def test_shape_residual(h16, oracle16, torch_mod):
