@@ -294,6 +294,22 @@ class SpectralRodIntegrator:
         _lib.check(self._lib.sri_project_onto_modes(self._h, batch, int(ne), _ptr(f, "f"), _ptr(out, "out")), "sri_project_onto_modes")
         return out
 
+    def galerkin_residual(self, K, H_diag, Q, m, M_tip, ne: int, K0=None, q0=None, out=None, reduce=None):
+        """g = int Phi^T (H (K - K0) - R(q)^T m) dX in one kernel (shape_residual + project_onto_modes, rho not stored);
+        reduce (2 doubles, optional) receives sum g^2 and max |g|, summed in a fixed order."""
+        self._follow_torch(K)
+        batch = K.shape[0]
+        H = np.ascontiguousarray(np.asarray(H_diag, dtype=np.float64))
+        if out is None:
+            out = _empty_like_kind(K, (batch, 3 * int(ne)))
+        _lib.check(
+            self._lib.sri_galerkin_residual(
+                self._h, batch, int(ne), _ptr(K, "K"), _ptr(K0, "K0"), H.ctypes.data, _ptr(Q, "Q"), _ptr(q0, "q0"),
+                _ptr(m, "m"), _ptr(M_tip, "M_tip"), _ptr(out, "g"), _ptr(reduce, "reduce")),
+            "sri_galerkin_residual",
+        )
+        return out
+
     def solve_small_batched(self, A, b, out=None, info=None):
         """A [batch][n][n] (row-major, destroyed), b [batch][n] -> x [batch][n]; CUDA tensors only."""
         self._follow_torch(A)

@@ -77,6 +77,9 @@ struct sri_context {
     double dmma_growth = sri::kDmmaGrowthDefault;
     bool use_dmma = false;
     bool wrench_configured = false;
+    double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
+    size_t partial_cap = 0;
+    unsigned* d_counter = nullptr;
     size_t tma_smem[3] = {0, 0, 0};  // last shared-memory size configured per TMA stage kernel, and its occupancy
     int tma_occ[3] = {0, 0, 0};
     size_t gtma_smem[3] = {0, 0, 0};  // the same for the 17 <= N <= 64 TMA stage kernels
@@ -299,6 +302,106 @@ __global__ void project_onto_modes_kernel(long long batch, int N, int ne, const 
         }
     }
     for (int k = 0; k < ne; ++k) out[bc * ne + k] = acc[k];
+}
+
+// g[b][c*ne+k] = sum_i w_i P_k(t_i) rho[b][c][i],  rho_i = H (K_i - K0_i) - R(q_i)^T m_i: shape_residual_kernel and
+// project_onto_modes_kernel in one pass (rho never reaches memory).  G lanes per rod (16 for N <= 16, else 32), node i in
+// lane i % G; the sums over the nodes are a shuffle tree.  Optional norms of g over the batch, reduced in a fixed order
+// (per block, then the last block to finish adds the block partials by index): bitwise reproducible.
+template <int G>
+__global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
+                                                                const double* __restrict__ ccw, const double* __restrict__ K,
+                                                                const double* __restrict__ K0, double h0, double h1, double h2,
+                                                                const double* __restrict__ Q, const double* __restrict__ q0,
+                                                                const double* __restrict__ m, const double* __restrict__ M_tip,
+                                                                double* __restrict__ g, double* __restrict__ partial,
+                                                                unsigned* __restrict__ counter, double* __restrict__ red) {
+    const int M = N - 1;
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    double acc[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = 0.0;
+    if (b < batch) {
+        for (int i = sub; i < N; i += G) {
+            sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+            if (i < M) { const double* s = Q + b * 4 * M + i; q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M]; }
+            else if (q0) { const double* s = q0 + b * 4; q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3]; }
+            double m0, m1, m2;
+            if (i == 0) { const double* s = M_tip + b * 3; m0 = s[0]; m1 = s[1]; m2 = s[2]; }
+            else { const double* s = m + b * 3 * M + (i - 1); m0 = s[0]; m1 = s[M]; m2 = s[2 * M]; }
+            double t0, t1, t2;
+            sri::q_rotate_T(q, m0, m1, m2, t0, t1, t2);
+            const double* kp = K + b * 3 * N + i;
+            double k0 = kp[0], k1 = kp[N], k2 = kp[2 * N];
+            if (K0) { const double* z = K0 + b * 3 * N + i; k0 -= z[0]; k1 -= z[N]; k2 -= z[2 * N]; }
+            const double w = ccw[i], t = tnodes[i];
+            const double wf[3] = {w * (h0 * k0 - t0), w * (h1 * k1 - t1), w * (h2 * k2 - t2)};
+            double pm = 1.0, pk = t;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c][0] = fma(wf[c], 1.0, acc[c][0]);
+            if (ne > 1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c][1] = fma(wf[c], pk, acc[c][1]);
+            }
+#pragma unroll
+            for (int k = 1; k < 7; ++k) {
+                if (k + 1 < ne) {
+                    const double pn = ((2 * k + 1) * t * pk - k * pm) / (k + 1);
+                    pm = pk; pk = pn;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[c][k + 1] = fma(wf[c], pk, acc[c][k + 1]);
+                }
+            }
+        }
+    }
+    double s2 = 0.0, mx = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < ne) {
+                double v = acc[c][k];
+#pragma unroll
+                for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                const int j = c * ne + k;
+                if (b < batch && sub == (j & (G - 1))) {
+                    g[b * 3 * ne + j] = v;
+                    s2 = fma(v, v, s2);
+                    mx = fmax(mx, fabs(v));
+                }
+            }
+        }
+    if (!red) return;
+    for (int off = 16; off >= 1; off >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    __shared__ double sh_s[8], sh_m[8];
+    __shared__ bool last;
+    const int w = threadIdx.x >> 5;
+    if (lane == 0) { sh_s[w] = s2; sh_m[w] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, z = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh_s[i]; z = fmax(z, sh_m[i]); }
+        partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = z;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && w == 0) {
+        __threadfence();
+        double a = 0.0, z = 0.0;
+        for (unsigned i = lane; i < gridDim.x; i += 32) { a += __ldcg(partial + 2 * i); z = fmax(z, __ldcg(partial + 2 * i + 1)); }
+        for (int off = 16; off >= 1; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            z = fmax(z, __shfl_xor_sync(0xffffffffu, z, off));
+        }
+        if (lane == 0) { red[0] = a; red[1] = z; *counter = 0u; }
+    }
 }
 
 // One thread per system: Gaussian elimination with partial pivoting, in place in global memory (row-major A).
@@ -973,6 +1076,8 @@ int sri_destroy(sri_handle h) {
     if (h->d_dtt) cudaFree(h->d_dtt);
     if (h->d_reduce) cudaFree(h->d_reduce);
     if (h->d_ccw) cudaFree(h->d_ccw);
+    if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_counter) cudaFree(h->d_counter);
     for (int sl = 0; sl < 4; ++sl)
         if (h->d_list[sl]) cudaFree(h->d_list[sl]);
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) {
@@ -1222,6 +1327,53 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
     const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
     const long long cap = (long long)h->sm_count;  // one CTA of 8 warps per SM (24 KB of shared memory per rod)
     sri::wrench_local_solve_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchWarps, sri::kWrenchSmem, h->stream>>>(p);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, const double* K0, const double* H_diag,
+                          const double* Q, const double* q0, const double* m, const double* M_tip, double* g,
+                          double* norm2_and_max) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!K || !H_diag || !Q || !m || !M_tip || !g)))
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_galerkin_residual: bad arguments (1 <= ne <= 8)");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    double H[3];
+    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
+    else std::memcpy(H, H_diag, sizeof(H));
+    Staging st(h);
+    const double *dK, *dK0, *dQ, *dq0, *dm, *dMt; double* dg; double* dred = nullptr;
+    SRI_TRY(st.in(K, (size_t)batch * 3 * N, &dK));
+    SRI_TRY(st.in(K0, (size_t)batch * 3 * N, &dK0));
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &dq0));
+    SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
+    SRI_TRY(st.out(g, (size_t)batch * 3 * ne, &dg));
+    const int G = N <= 16 ? 16 : 32;
+    const long long blocks = ((long long)batch * G + 255) / 256;
+    if (norm2_and_max) {
+        SRI_TRY(st.out(norm2_and_max, 2, &dred));
+        if (!h->d_counter) {
+            SRI_CUDA(cudaMalloc(&h->d_counter, sizeof(unsigned)));
+            SRI_CUDA(cudaMemset(h->d_counter, 0, sizeof(unsigned)));
+        }
+        if ((size_t)blocks > h->partial_cap) {  // (grows outside stream capture: the first, eager call of a shape sizes it)
+            size_t cap = h->partial_cap ? h->partial_cap : 4096;
+            while (cap < (size_t)blocks) cap *= 2;
+            SRI_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->d_partial) SRI_CUDA(cudaFree(h->d_partial));
+            h->d_partial = nullptr; h->partial_cap = 0;
+            SRI_CUDA(cudaMalloc(&h->d_partial, cap * 2 * sizeof(double)));
+            h->partial_cap = cap;
+        }
+    }
+    if (G == 16)
+        galerkin_residual_kernel<16><<<(unsigned)blocks, 256, 0, h->stream>>>(batch, N, ne, h->d_tnodes, h->d_ccw, dK, dK0, H[0], H[1], H[2], dQ, dq0, dm, dMt, dg, h->d_partial, h->d_counter, dred);
+    else
+        galerkin_residual_kernel<32><<<(unsigned)blocks, 256, 0, h->stream>>>(batch, N, ne, h->d_tnodes, h->d_ccw, dK, dK0, H[0], H[1], H[2], dQ, dq0, dm, dMt, dg, h->d_partial, h->d_counter, dred);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();

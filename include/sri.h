@@ -159,6 +159,15 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
  * Clenshaw-Curtis weights of the N Chebyshev nodes on [0,1].  f [batch][3][N] -> out [batch][3*ne]. */
 int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f, double* out);
 
+/* Galerkin residual of the static shape problem in one pass (rod_modeling.pdf eq. 1.25 projected as in 2.14/2.20):
+ *   g[b][c*ne+k] = sum_i w_i P_k(2 x_i - 1) rho[b][c][i],   rho_i = H (K_i - K0_i) - R(q_i)^T m_i,
+ * i.e. sri_shape_residual followed by sri_project_onto_modes without storing rho.  Arguments as in those two;
+ * g [batch][3*ne]; norm2_and_max (2 doubles or NULL): sum g^2 and max |g| over the batch, reduced in a fixed order
+ * (bitwise reproducible from run to run). */
+int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, const double* K0, const double* H_diag,
+                          const double* Q, const double* q0, const double* m, const double* M_tip, double* g,
+                          double* norm2_and_max);
+
 /* Batched dense solve A x = b for small systems (n <= 24), partial pivoting, one rod per thread: the Newton step
  * of the static shape problem.  A [batch][n][n] row-major (destroyed), b [batch][n] -> x [batch][n].
  * info [batch] or NULL as in sri_integrate_quaternions.  Device pointers only. */

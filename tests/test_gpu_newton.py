@@ -142,3 +142,66 @@ def test_newton_cuda_graph_replay_equals_eager_and_is_reused(h16, torch_mod):
     out = h16.integrate_all(K, tF[:4], tM[:4])
     h16.synchronize()
     assert np.isfinite(out["Q"].cpu().numpy()).all()
+
+
+def test_newton_batched_jacobian_equals_column_by_column(h16, torch_mod):
+    """jacobian="batched" integrates the 3 ne perturbed copies of the batch in one call of the hot path; every rod goes
+    through the same kernels as in the column-by-column loop, so the iterates must be identical (with and without K0)."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200.newton import StaticShapeSolver
+    B, ne = 333, 3
+    rng = np.random.default_rng(11)
+    F = np.zeros((B, 3)); F[:, 2] = -rng.uniform(0.1, 2.0, size=B)
+    Mt = rng.uniform(-0.1, 0.1, size=(B, 3))
+    K0 = 0.2 * rng.normal(size=(B, 3, 1)) * np.ones((1, 1, 16))
+    tF, tM, tK0 = (torch_mod.from_numpy(np.ascontiguousarray(a)).cuda() for a in (F, Mt, K0))
+    for k0 in (None, tK0):
+        for use_graph in (False, True):
+            cols = StaticShapeSolver(h16, (1.0, 1.0, 0.77), ne=ne, jacobian="columns")
+            wide = StaticShapeSolver(h16, (1.0, 1.0, 0.77), ne=ne, jacobian="batched")
+            q_c, rep_c = cols.solve(tF, tM, K0=k0, use_graph=use_graph)
+            q_w, rep_w = wide.solve(tF, tM, K0=k0, use_graph=use_graph)
+            assert rep_c.converged and rep_w.converged and rep_w.iterations == rep_c.iterations
+            assert rep_w.integrations == rep_c.integrations
+            assert torch_mod.equal(q_c, q_w)
+
+
+@pytest.mark.parametrize("N", [16, 9, 32])
+def test_galerkin_residual_equals_residual_then_projection(sri_lib, make_oracle, torch_mod, N):
+    """sri_galerkin_residual = sri_project_onto_modes(sri_shape_residual(...)) without the nodal residual in memory: against
+    the oracle's residual projected with numpy, against the two-kernel composition on the GPU, and its norms (fixed summation
+    order: bitwise reproducible)."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    o = make_oracle(N)
+    rng = np.random.default_rng(60 + N)
+    B = 1237
+    K, F, Mt, fb = o.generate_rods(0x5EED, 77, B)
+    ref = o.integrate_all(K, F, Mt, fbar=fb)
+    K0 = 0.3 * rng.normal(size=(B, 3, N))
+    q0 = None
+    H = np.array([1.0, 0.9, 0.77])
+    x = o.chebyshev_points()
+    w = cc_weights(N)
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    with SpectralRodIntegrator(N, 0) as h:
+        for ne, k0 in ((3, K0), (1, None), (8, K0)):
+            rho_ref = o.shape_residual(K, H, ref["Q"], ref["m"], Mt, K0=k0)
+            g_ref = np.einsum("bci,ki,i->bck", rho_ref, legendre_table(ne, 2 * x - 1), w).reshape(B, 3 * ne)
+            red = torch_mod.full((2,), -1.0, dtype=torch_mod.float64, device="cuda")
+            tk0 = None if k0 is None else t(k0)
+            g = h.galerkin_residual(t(K), H, t(ref["Q"]), t(ref["m"]), t(Mt), ne, K0=tk0, reduce=red)
+            g2 = h.project_onto_modes(h.shape_residual(t(K), H, t(ref["Q"]), t(ref["m"]), t(Mt), K0=tk0), ne)
+            red_again = torch_mod.zeros(2, dtype=torch_mod.float64, device="cuda")
+            g_again = h.galerkin_residual(t(K), H, t(ref["Q"]), t(ref["m"]), t(Mt), ne, K0=tk0, reduce=red_again)
+            h.synchronize()
+            g, g2, red = g.cpu().numpy(), g2.cpu().numpy(), red.cpu().numpy()
+            scale = np.abs(g_ref).max()
+            assert np.abs(g - g_ref).max() <= 1e-13 * scale
+            assert np.abs(g - g2).max() <= 1e-14 * scale
+            assert abs(red[0] - (g ** 2).sum()) <= 1e-13 * (g ** 2).sum() and red[1] == np.abs(g).max()
+            assert torch_mod.equal(g_again.cpu(), torch_mod.from_numpy(g)) and (red_again.cpu().numpy() == red).all()
+        # host buffers
+        g_host = h.galerkin_residual(K[:7], H, ref["Q"][:7], ref["m"][:7], Mt[:7], 3)
+        h.synchronize()
+    rho_ref = o.shape_residual(K[:7], H, ref["Q"][:7], ref["m"][:7], Mt[:7])
+    g_ref = np.einsum("bci,ki,i->bck", rho_ref, legendre_table(3, 2 * x - 1), w).reshape(7, 9)
+    assert np.abs(g_host - g_ref).max() <= 1e-13 * np.abs(g_ref).max()

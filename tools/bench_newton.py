@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rods", type=int, default=100000)
 ap.add_argument("--ne", type=int, default=3)
 ap.add_argument("--N", type=int, default=16)
+ap.add_argument("--jacobian", default="batched", choices=("batched", "columns"))
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -32,7 +33,7 @@ F = torch.empty((B, 3), dtype=torch.float64, device=dev)
 h.generate_rods(0x5EED, lo, B, None, F, None, None)
 F[:, 2] = -(F[:, 2] + 1.0); F[:, :2] = 0.0
 Mt = torch.zeros((B, 3), dtype=torch.float64, device=dev)
-solver = StaticShapeSolver(h, (1.0, 1.0, 0.77), ne=args.ne)
+solver = StaticShapeSolver(h, (1.0, 1.0, 0.77), ne=args.ne, jacobian=args.jacobian)
 # first solve of this shape: runs one iteration eagerly, captures the iteration into a CUDA graph, replays it (every rank
 # takes part, so the collectives match); the timed solve below replays the cached graph from its first iteration on
 torch.cuda.synchronize()
@@ -52,7 +53,7 @@ torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
 if world > 1: dist.all_reduce(dt, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"config": "cfg5 Newton static shape", "rods_total": args.rods, "n_gpus": world, "N": args.N, "ne": args.ne,
+    print(json.dumps({"config": "cfg5 Newton static shape", "rods_total": args.rods, "n_gpus": world, "N": args.N, "ne": args.ne, "jacobian": args.jacobian,
                       "converged": rep.converged, "newton_iterations": rep.iterations, "integrations_of_the_batch": rep.integrations,
                       "seconds": float(dt.item()), "seconds_eager_launches": eager, "seconds_first_solve_with_capture": first, "rod_solves_per_s": args.rods / float(dt.item()),
                       "rod_integrations_per_s": args.rods * rep.integrations / float(dt.item()),
