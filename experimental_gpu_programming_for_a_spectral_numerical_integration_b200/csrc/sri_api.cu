@@ -71,12 +71,13 @@ struct sri_context {
     double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
+    double* d_ptab = nullptr;    // Legendre polynomials at the nodes, P_k(2 x_i - 1), [8][N]
     int fused_blocks_per_sm = 0;
     int stage_blocks_per_sm = 0;
     int dmma_blocks_per_sm = 0;
     double dmma_growth = sri::kDmmaGrowthDefault;
     bool use_dmma = false;
-    bool wrench_configured = false;
+    bool wrench_configured = false, solve_small_configured = false;
     double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
     size_t partial_cap = 0;
     unsigned* d_counter = nullptr;
@@ -187,6 +188,37 @@ __global__ void strain_from_modes_kernel(long long batch, int N, int ne, const d
         acc = fma(p, q[k + 1], acc);
     }
     K[idx] = acc;
+}
+
+// P_k(t_i), k < 8, by the recurrence of utilities.h:59 -- once per handle; [k][N]
+__global__ void legendre_table_kernel(int N, const double* __restrict__ tnodes, double* __restrict__ ptab) {
+    const int i = threadIdx.x;
+    if (i >= N) return;
+    const double t = tnodes[i];
+    double pm = 1.0, p = t;
+    ptab[i] = 1.0;
+    ptab[N + i] = t;
+    for (int k = 1; k + 1 < 8; ++k) {
+        const double pn = ((2 * k + 1) * t * p - k * pm) / (k + 1);
+        pm = p;
+        p = pn;
+        ptab[(k + 1) * N + i] = p;
+    }
+}
+
+// strain_from_modes for ne <= 8 with the cached Legendre table: NL (a power of two >= N) lanes per (rod, component), no
+// integer division, no recurrence; same order of the additions as strain_from_modes_kernel.
+template <int NL>
+__global__ void __launch_bounds__(256) strain_from_modes_table_kernel(long long rows /* batch*3 */, int N, int ne,
+                                                                      const double* __restrict__ ptab,
+                                                                      const double* __restrict__ qe, double* __restrict__ K) {
+    const int i = threadIdx.x & (NL - 1);
+    const long long bc = (long long)blockIdx.x * (256 / NL) + (threadIdx.x / NL);
+    if (bc >= rows || i >= N) return;
+    const double* q = qe + bc * ne;
+    double acc = q[0];
+    for (int k = 1; k < ne; ++k) acc = fma(ptab[k * N + i], q[k], acc);
+    K[bc * N + i] = acc;
 }
 
 // rho = H (K - K0) - R(q)^T m at all N nodes; block-reduced sum(rho^2) and max|rho| via atomics.
@@ -308,22 +340,23 @@ __global__ void project_onto_modes_kernel(long long batch, int N, int ne, const 
 // project_onto_modes_kernel in one pass (rho never reaches memory).  G lanes per rod (16 for N <= 16, else 32), node i in
 // lane i % G; the sums over the nodes are a shuffle tree.  Optional norms of g over the batch, reduced in a fixed order
 // (per block, then the last block to finish adds the block partials by index): bitwise reproducible.
-template <int G>
-__global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
+template <int G, int NE>
+__global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch, int N, const double* __restrict__ ptab,
                                                                 const double* __restrict__ ccw, const double* __restrict__ K,
                                                                 const double* __restrict__ K0, double h0, double h1, double h2,
                                                                 const double* __restrict__ Q, const double* __restrict__ q0,
                                                                 const double* __restrict__ m, const double* __restrict__ M_tip,
                                                                 double* __restrict__ g, double* __restrict__ partial,
                                                                 unsigned* __restrict__ counter, double* __restrict__ red) {
+    constexpr int ne = NE;
     const int M = N - 1;
     const int lane = threadIdx.x & 31, sub = lane & (G - 1);
     const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    double acc[3][8];
+    double acc[3][NE];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[c][k] = 0.0;
+        for (int k = 0; k < NE; ++k) acc[c][k] = 0.0;
     if (b < batch) {
         for (int i = sub; i < N; i += G) {
             sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
@@ -337,23 +370,13 @@ __global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch,
             const double* kp = K + b * 3 * N + i;
             double k0 = kp[0], k1 = kp[N], k2 = kp[2 * N];
             if (K0) { const double* z = K0 + b * 3 * N + i; k0 -= z[0]; k1 -= z[N]; k2 -= z[2 * N]; }
-            const double w = ccw[i], t = tnodes[i];
+            const double w = ccw[i];
             const double wf[3] = {w * (h0 * k0 - t0), w * (h1 * k1 - t1), w * (h2 * k2 - t2)};
-            double pm = 1.0, pk = t;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c][0] = fma(wf[c], 1.0, acc[c][0]);
-            if (ne > 1) {
+            for (int k = 0; k < NE; ++k) {
+                const double pk = ptab[k * N + i];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) acc[c][1] = fma(wf[c], pk, acc[c][1]);
-            }
-#pragma unroll
-            for (int k = 1; k < 7; ++k) {
-                if (k + 1 < ne) {
-                    const double pn = ((2 * k + 1) * t * pk - k * pm) / (k + 1);
-                    pm = pk; pk = pn;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[c][k + 1] = fma(wf[c], pk, acc[c][k + 1]);
-                }
+                for (int c = 0; c < 3; ++c) acc[c][k] = fma(wf[c], pk, acc[c][k]);
             }
         }
     }
@@ -361,8 +384,8 @@ __global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch,
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < ne) {
+        for (int k = 0; k < NE; ++k) {
+            {
                 double v = acc[c][k];
 #pragma unroll
                 for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -404,38 +427,52 @@ __global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch,
     }
 }
 
-// One thread per system: Gaussian elimination with partial pivoting, in place in global memory (row-major A).
-__global__ void solve_small_kernel(long long batch, int n, double* __restrict__ A, const double* __restrict__ b,
+// One thread per system: Gaussian elimination with partial pivoting.  The block's systems (contiguous in global memory)
+// are staged in shared memory element-major, a[e * (T + 1) + thread]: coalesced copies, conflict-free in both phases.
+__global__ void solve_small_kernel(long long batch, int n, const double* __restrict__ A, const double* __restrict__ b,
                                    double* __restrict__ x, int* __restrict__ info) {
-    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= batch) return;
-    double* a = A + s * n * n;
-    double rhs[24];
-    for (int i = 0; i < n; ++i) rhs[i] = b[s * n + i];
+    extern __shared__ double ssm[];
+    const int T = blockDim.x, LD = T + 1, tid = threadIdx.x, nn = n * n;
+    const long long s0 = (long long)blockIdx.x * T;
+    const int count = (int)((batch - s0) < T ? (batch - s0) : T);
+    double* a = ssm + tid;           // a[e * LD]: this thread's matrix, row-major element e
+    double* rhs = ssm + nn * LD + tid;
+    {
+        const double* src = A + s0 * nn;
+        for (int e = tid; e < count * nn; e += T) { const int sys = e / nn, el = e - sys * nn; ssm[el * LD + sys] = src[e]; }
+        const double* bs = b + s0 * n;
+        for (int e = tid; e < count * n; e += T) { const int sys = e / n, el = e - sys * n; ssm[(nn + el) * LD + sys] = bs[e]; }
+    }
+    __syncthreads();
     int bad = 0;
-    for (int k = 0; k < n; ++k) {
-        int p = k;
-        double best = fabs(a[k * n + k]);
-        for (int i = k + 1; i < n; ++i) { const double v = fabs(a[i * n + k]); if (v > best) { best = v; p = i; } }
-        if (best == 0.0) { if (!bad) bad = k + 1; continue; }
-        if (p != k) {
-            for (int j = k; j < n; ++j) { const double t = a[k * n + j]; a[k * n + j] = a[p * n + j]; a[p * n + j] = t; }
-            const double t = rhs[k]; rhs[k] = rhs[p]; rhs[p] = t;
+    if (tid < count) {
+        for (int k = 0; k < n; ++k) {
+            int p = k;
+            double best = fabs(a[(k * n + k) * LD]);
+            for (int i = k + 1; i < n; ++i) { const double v = fabs(a[(i * n + k) * LD]); if (v > best) { best = v; p = i; } }
+            if (best == 0.0) { if (!bad) bad = k + 1; continue; }
+            if (p != k) {
+                for (int j = k; j < n; ++j) { const double t = a[(k * n + j) * LD]; a[(k * n + j) * LD] = a[(p * n + j) * LD]; a[(p * n + j) * LD] = t; }
+                const double t = rhs[k * LD]; rhs[k * LD] = rhs[p * LD]; rhs[p * LD] = t;
+            }
+            const double inv = 1.0 / a[(k * n + k) * LD];
+            const double rk = rhs[k * LD];
+            for (int i = k + 1; i < n; ++i) {
+                const double l = a[(i * n + k) * LD] * inv;
+                for (int j = k + 1; j < n; ++j) a[(i * n + j) * LD] = fma(-l, a[(k * n + j) * LD], a[(i * n + j) * LD]);
+                rhs[i * LD] = fma(-l, rk, rhs[i * LD]);
+            }
         }
-        const double inv = 1.0 / a[k * n + k];
-        for (int i = k + 1; i < n; ++i) {
-            const double l = a[i * n + k] * inv;
-            for (int j = k + 1; j < n; ++j) a[i * n + j] = fma(-l, a[k * n + j], a[i * n + j]);
-            rhs[i] = fma(-l, rhs[k], rhs[i]);
+        for (int k = n - 1; k >= 0; --k) {
+            double v = rhs[k * LD];
+            for (int j = k + 1; j < n; ++j) v = fma(-a[(k * n + j) * LD], rhs[j * LD], v);
+            rhs[k * LD] = v / a[(k * n + k) * LD];
         }
+        if (info) info[s0 + tid] = bad;
     }
-    for (int k = n - 1; k >= 0; --k) {
-        double v = rhs[k];
-        for (int j = k + 1; j < n; ++j) v = fma(-a[k * n + j], rhs[j], v);
-        rhs[k] = v / a[k * n + k];
-    }
-    for (int i = 0; i < n; ++i) x[s * n + i] = rhs[i];
-    if (info) info[s] = bad;
+    __syncthreads();
+    double* xs = x + s0 * n;
+    for (int e = tid; e < count * n; e += T) { const int sys = e / n, el = e - sys * n; xs[e] = ssm[(nn + el) * LD + sys]; }
 }
 
 // SURVEY 8(d) synthetic rods.  One thread per rod.
@@ -1025,6 +1062,10 @@ int sri_create(int N, int device, sri_handle* out) {
         for (int i = 0; i < N; ++i) t[i] = 2 * h->ops.x[i] - 1;
         SRI_CUDA(cudaMalloc(&h->d_tnodes, sizeof(double) * N));
         SRI_CUDA(cudaMemcpy(h->d_tnodes, t.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+        SRI_CUDA(cudaMalloc(&h->d_ptab, sizeof(double) * 8 * N));
+        legendre_table_kernel<<<1, 64>>>(N, h->d_tnodes, h->d_ptab);
+        SRI_CUDA(cudaGetLastError());
+        SRI_CUDA(cudaDeviceSynchronize());
     }
     {
         std::vector<double> t((size_t)M * M + M);
@@ -1076,6 +1117,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_dtt) cudaFree(h->d_dtt);
     if (h->d_reduce) cudaFree(h->d_reduce);
     if (h->d_ccw) cudaFree(h->d_ccw);
+    if (h->d_ptab) cudaFree(h->d_ptab);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_counter) cudaFree(h->d_counter);
     for (int sl = 0; sl < 4; ++sl)
@@ -1140,7 +1182,14 @@ int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe,
     SRI_TRY(st.in(qe, (size_t)batch * 3 * ne, &dqe));
     SRI_TRY(st.out(K, (size_t)batch * 3 * h->N, &dK));
     const long long total = (long long)batch * 3 * h->N;
-    strain_from_modes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, dqe, dK);
+    if (ne <= 8) {
+        const long long rows = (long long)batch * 3;
+        if (h->N <= 16) strain_from_modes_table_kernel<16><<<(unsigned)((rows + 15) / 16), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK);
+        else if (h->N <= 32) strain_from_modes_table_kernel<32><<<(unsigned)((rows + 7) / 8), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK);
+        else strain_from_modes_table_kernel<64><<<(unsigned)((rows + 3) / 4), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK);
+    } else {
+        strain_from_modes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, dqe, dK);
+    }
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();
@@ -1370,10 +1419,19 @@ int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, 
             h->partial_cap = cap;
         }
     }
-    if (G == 16)
-        galerkin_residual_kernel<16><<<(unsigned)blocks, 256, 0, h->stream>>>(batch, N, ne, h->d_tnodes, h->d_ccw, dK, dK0, H[0], H[1], H[2], dQ, dq0, dm, dMt, dg, h->d_partial, h->d_counter, dred);
-    else
-        galerkin_residual_kernel<32><<<(unsigned)blocks, 256, 0, h->stream>>>(batch, N, ne, h->d_tnodes, h->d_ccw, dK, dK0, H[0], H[1], H[2], dQ, dq0, dm, dMt, dg, h->d_partial, h->d_counter, dred);
+#define SRI_GALERKIN(GG, NE_)                                                                                            \
+    galerkin_residual_kernel<GG, NE_><<<(unsigned)blocks, 256, 0, h->stream>>>(batch, N, h->d_ptab, h->d_ccw, dK, dK0, H[0], \
+                                                                                 H[1], H[2], dQ, dq0, dm, dMt, dg,          \
+                                                                                 h->d_partial, h->d_counter, dred)
+#define SRI_GALERKIN_NE(GG)                                                                                              \
+    switch (ne) {                                                                                                        \
+        case 1: SRI_GALERKIN(GG, 1); break; case 2: SRI_GALERKIN(GG, 2); break; case 3: SRI_GALERKIN(GG, 3); break;      \
+        case 4: SRI_GALERKIN(GG, 4); break; case 5: SRI_GALERKIN(GG, 5); break; case 6: SRI_GALERKIN(GG, 6); break;      \
+        case 7: SRI_GALERKIN(GG, 7); break; default: SRI_GALERKIN(GG, 8); break;                                        \
+    }
+    if (G == 16) { SRI_GALERKIN_NE(16) } else { SRI_GALERKIN_NE(32) }
+#undef SRI_GALERKIN_NE
+#undef SRI_GALERKIN
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();
@@ -1400,7 +1458,13 @@ int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const
     if (batch == 0) return SRI_OK;
     for (const void* p : {(const void*)A, (const void*)b, (const void*)x, (const void*)info})
         if (p && !is_device_pointer(p)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: device pointers only");
-    solve_small_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(batch, n, A, b, x, info);
+    const int T = n <= 13 ? 128 : (n <= 19 ? 64 : 32);
+    const size_t smem = (size_t)(n * n + n) * (T + 1) * sizeof(double);
+    if (!h->solve_small_configured) {
+        SRI_CUDA(cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        h->solve_small_configured = true;
+    }
+    solve_small_kernel<<<(unsigned)((batch + T - 1) / T), T, smem, h->stream>>>(batch, n, A, b, x, info);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return SRI_OK;

@@ -169,7 +169,7 @@ int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, 
                           double* norm2_and_max);
 
 /* Batched dense solve A x = b for small systems (n <= 24), partial pivoting, one rod per thread: the Newton step
- * of the static shape problem.  A [batch][n][n] row-major (destroyed), b [batch][n] -> x [batch][n].
+ * of the static shape problem.  A [batch][n][n] row-major (may be overwritten), b [batch][n] -> x [batch][n].
  * info [batch] or NULL as in sri_integrate_quaternions.  Device pointers only. */
 int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const double* b, double* x, int* info);
 
