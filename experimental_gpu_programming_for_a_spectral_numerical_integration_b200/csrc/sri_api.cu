@@ -341,7 +341,7 @@ __global__ void project_onto_modes_kernel(long long batch, int N, int ne, const 
 // lane i % G; the sums over the nodes are a shuffle tree.  Optional norms of g over the batch, reduced in a fixed order
 // (per block, then the last block to finish adds the block partials by index): bitwise reproducible.
 template <int G, int NE>
-__global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch, int N, const double* __restrict__ ptab,
+__global__ void __launch_bounds__(256, 4) galerkin_residual_kernel(long long batch, int N, const double* __restrict__ ptab,
                                                                 const double* __restrict__ ccw, const double* __restrict__ K,
                                                                 const double* __restrict__ K0, double h0, double h1, double h2,
                                                                 const double* __restrict__ Q, const double* __restrict__ q0,
@@ -359,17 +359,21 @@ __global__ void __launch_bounds__(256) galerkin_residual_kernel(long long batch,
         for (int k = 0; k < NE; ++k) acc[c][k] = 0.0;
     if (b < batch) {
         for (int i = sub; i < N; i += G) {
-            sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
-            if (i < M) { const double* s = Q + b * 4 * M + i; q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M]; }
-            else if (q0) { const double* s = q0 + b * 4; q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3]; }
-            double m0, m1, m2;
-            if (i == 0) { const double* s = M_tip + b * 3; m0 = s[0]; m1 = s[1]; m2 = s[2]; }
-            else { const double* s = m + b * 3 * M + (i - 1); m0 = s[0]; m1 = s[M]; m2 = s[2 * M]; }
-            double t0, t1, t2;
-            sri::q_rotate_T(q, m0, m1, m2, t0, t1, t2);
+            // every load is issued before the first use: pointers are selected, not branched on (the kernel is bound by the
+            // latency of these loads)
+            const bool inner = i < M;
+            const double* qs = inner ? Q + b * 4 * M + i : (q0 ? q0 + b * 4 : nullptr);
+            const int qst = inner ? M : 1;
+            const double* ms = i == 0 ? M_tip + b * 3 : m + b * 3 * M + (i - 1);
+            const int mst = i == 0 ? 1 : M;
             const double* kp = K + b * 3 * N + i;
+            sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+            if (qs) { q.w = qs[0]; q.x = qs[qst]; q.y = qs[2 * qst]; q.z = qs[3 * qst]; }
+            const double m0 = ms[0], m1 = ms[mst], m2 = ms[2 * mst];
             double k0 = kp[0], k1 = kp[N], k2 = kp[2 * N];
             if (K0) { const double* z = K0 + b * 3 * N + i; k0 -= z[0]; k1 -= z[N]; k2 -= z[2 * N]; }
+            double t0, t1, t2;
+            sri::q_rotate_T(q, m0, m1, m2, t0, t1, t2);
             const double w = ccw[i];
             const double wf[3] = {w * (h0 * k0 - t0), w * (h1 * k1 - t1), w * (h2 * k2 - t2)};
 #pragma unroll

@@ -16,6 +16,7 @@ all-reduce of [sum g^2, max |g|] per iteration (sharding.allreduce_residual).
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -153,9 +154,10 @@ class StaticShapeSolver:
         rep.integrations += 1
         for it in range(max_iter + 1):
             allreduce_residual(red, group)                     # the only collective: 16 bytes per iteration
-            rms = float((red[0] / total_dof).sqrt().item())
+            sum2, gmax = red.tolist()                          # one device-to-host read per iteration
+            rms = math.sqrt(sum2 / total_dof) if sum2 == sum2 else float("nan")
             rep.rms_history.append(rms)
-            rep.max_history.append(float(red[1].item()))
+            rep.max_history.append(gmax)
             if rms < tol:
                 rep.converged = True
                 break
