@@ -63,6 +63,7 @@ SYMBOLS = {
     "sri_integrate_wrench_local": (c_int, [c_void_p, c_int64] + [c_void_p] * 10),
     "sri_project_onto_modes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "sri_galerkin_residual": (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 9),
+    "sri_generalised_forces": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "sri_solve_small_batched": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_generate_rods": (c_int, [c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_last_error_string": (c_char_p, []),

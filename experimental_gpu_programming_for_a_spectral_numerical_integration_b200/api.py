@@ -310,6 +310,15 @@ class SpectralRodIntegrator:
         )
         return out
 
+    def generalised_forces(self, Lambda, ne: int, out=None):
+        """Q_ad = -int Phi^T (couple part of the local-frame wrench) dX  (rod_modeling.pdf eqs. 2.16, 2.20)."""
+        self._follow_torch(Lambda)
+        batch = Lambda.shape[0]
+        if out is None:
+            out = _empty_like_kind(Lambda, (batch, 3 * int(ne)))
+        _lib.check(self._lib.sri_generalised_forces(self._h, batch, int(ne), _ptr(Lambda, "Lambda"), _ptr(out, "Qad")), "sri_generalised_forces")
+        return out
+
     def solve_small_batched(self, A, b, out=None, info=None):
         """A [batch][n][n] (row-major, destroyed), b [batch][n] -> x [batch][n]; CUDA tensors only."""
         self._follow_torch(A)

@@ -313,27 +313,26 @@ __global__ void wrench_local_kernel(long long batch, int N, const double* __rest
     d[0] = c0; d[N] = c1; d[2 * N] = c2; d[3 * N] = f0; d[4 * N] = f1; d[5 * N] = f2;
 }
 
-// out[b][c*ne+k] = sum_i w_i P_k(t_i) f[b][c][i]: one thread per (rod, component), Legendre recurrence per node.
-__global__ void project_onto_modes_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
-                                          const double* __restrict__ ccw, const double* __restrict__ f,
-                                          double* __restrict__ out) {
+// out[b][c*ne+k] = scale * sum_i w_i P_k(t_i) f[b*rod_stride + c*N + i]: one thread per (rod, component), cached Legendre
+// table.  rod_stride = 3 N, scale = 1: projection of a nodal field; rod_stride = 6 N, scale = -1: generalised forces of the
+// couple part of a wrench field.
+__global__ void project_onto_modes_kernel(long long batch, int N, int ne, long long rod_stride, double scale,
+                                          const double* __restrict__ ptab, const double* __restrict__ ccw,
+                                          const double* __restrict__ f, double* __restrict__ out) {
     const long long bc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (bc >= batch * 3) return;
+    const long long b = bc / 3;
+    const int c = (int)(bc - 3 * b);
     double acc[8];
     for (int k = 0; k < ne; ++k) acc[k] = 0.0;
-    const double* fi = f + bc * N;
+    const double* fi = f + b * rod_stride + c * N;
     for (int i = 0; i < N; ++i) {
-        const double t = tnodes[i], wf = ccw[i] * fi[i];
-        double pm = 1.0, p = t;
-        acc[0] = fma(wf, 1.0, acc[0]);
-        if (ne > 1) acc[1] = fma(wf, p, acc[1]);
-        for (int k = 1; k + 1 < ne; ++k) {
-            const double pn = ((2 * k + 1) * t * p - k * pm) / (k + 1);
-            pm = p; p = pn;
-            acc[k + 1] = fma(wf, p, acc[k + 1]);
-        }
+        const double wf = ccw[i] * fi[i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < ne) acc[k] = fma(wf, ptab[k * N + i], acc[k]);
     }
-    for (int k = 0; k < ne; ++k) out[bc * ne + k] = acc[k];
+    for (int k = 0; k < ne; ++k) out[bc * ne + k] = scale * acc[k];
 }
 
 // g[b][c*ne+k] = sum_i w_i P_k(t_i) rho[b][c][i],  rho_i = H (K_i - K0_i) - R(q_i)^T m_i: shape_residual_kernel and
@@ -1450,7 +1449,22 @@ int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f,
     SRI_TRY(st.in(f, (size_t)batch * 3 * h->N, &df));
     SRI_TRY(st.out(out, (size_t)batch * 3 * ne, &dout));
     const long long total = (long long)batch * 3;
-    project_onto_modes_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, h->d_ccw, df, dout);
+    project_onto_modes_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(batch, h->N, ne, 3LL * h->N, 1.0, h->d_ptab, h->d_ccw, df, dout);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
+int sri_generalised_forces(sri_handle h, int64_t batch, int ne, const double* Lambda, double* Qad) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!Lambda || !Qad))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_generalised_forces: bad arguments (1 <= ne <= 8)");
+    if (batch == 0) return SRI_OK;
+    Staging st(h);
+    const double* dL; double* dout;
+    SRI_TRY(st.in(Lambda, (size_t)batch * 6 * h->N, &dL));
+    SRI_TRY(st.out(Qad, (size_t)batch * 3 * ne, &dout));
+    const long long total = (long long)batch * 3;
+    project_onto_modes_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(batch, h->N, ne, 6LL * h->N, -1.0, h->d_ptab, h->d_ccw, dL, dout);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();

@@ -159,6 +159,12 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
  * Clenshaw-Curtis weights of the N Chebyshev nodes on [0,1].  f [batch][3][N] -> out [batch][3*ne]. */
 int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f, double* out);
 
+/* Generalised internal forces of the angular strain modes (rod_modeling.pdf eqs. 2.16, 2.20: Q_ad = -int Phi^T B^T Lambda dX
+ * with B^T Lambda = the couple part of the local-frame wrench): Qad[b][c*ne+k] = -sum_i w_i P_k(2 x_i - 1) Lambda[b][c][i],
+ * c = 0..2.  Lambda [batch][6][N] as written by sri_wrench_local / sri_integrate_wrench_local -> Qad [batch][3*ne].  The
+ * static balance 2.20 reads  int Phi^T H (K - K0) dX + Qad = 0. */
+int sri_generalised_forces(sri_handle h, int64_t batch, int ne, const double* Lambda, double* Qad);
+
 /* Galerkin residual of the static shape problem in one pass (rod_modeling.pdf eq. 1.25 projected as in 2.14/2.20):
  *   g[b][c*ne+k] = sum_i w_i P_k(2 x_i - 1) rho[b][c][i],   rho_i = H (K_i - K0_i) - R(q_i)^T m_i,
  * i.e. sri_shape_residual followed by sri_project_onto_modes without storing rho.  Arguments as in those two;

@@ -205,3 +205,30 @@ def test_galerkin_residual_equals_residual_then_projection(sri_lib, make_oracle,
     rho_ref = o.shape_residual(K[:7], H, ref["Q"][:7], ref["m"][:7], Mt[:7])
     g_ref = np.einsum("bci,ki,i->bck", rho_ref, legendre_table(3, 2 * x - 1), w).reshape(7, 9)
     assert np.abs(g_host - g_ref).max() <= 1e-13 * np.abs(g_ref).max()
+
+
+def test_generalised_forces_close_the_static_balance(h16, oracle16, torch_mod):
+    """rod_modeling.pdf eq. 2.20: the Galerkin residual is the stiffness term plus the generalised internal forces,
+    g = int Phi^T H (K - K0) dX + Q_ad, with Q_ad = -int Phi^T (couple part of the local-frame wrench)."""
+    B, ne = 211, 4
+    rng = np.random.default_rng(70)
+    K, F, Mt, fb = oracle16.generate_rods(0x5EED, 500, B)
+    ref = oracle16.integrate_all(K, F, Mt, fbar=fb)
+    K0 = 0.1 * rng.normal(size=(B, 3, 16))
+    H = np.array([1.0, 0.9, 0.77])
+    x = oracle16.chebyshev_points()
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    lam = h16.wrench_local(t(ref["Q"]), t(ref["n"]), t(ref["m"]), t(F), t(Mt))
+    qad = h16.generalised_forces(lam, ne)
+    g = h16.galerkin_residual(t(K), H, t(ref["Q"]), t(ref["m"]), t(Mt), ne, K0=t(K0))
+    stiff = h16.project_onto_modes(t(H[None, :, None] * (K - K0)), ne)
+    h16.synchronize()
+    lam_np = lam.cpu().numpy()
+    ref_qad = -np.einsum("bci,ki,i->bck", lam_np[:, :3, :], legendre_table(ne, 2 * x - 1), cc_weights(16)).reshape(B, 3 * ne)
+    assert np.abs(qad.cpu().numpy() - ref_qad).max() <= 1e-14 * np.abs(ref_qad).max()
+    total = (stiff + qad).cpu().numpy()
+    assert np.abs(total - g.cpu().numpy()).max() <= 1e-13 * np.abs(total).max()
+    # host buffers
+    qad_host = h16.generalised_forces(lam_np[:9], ne)
+    h16.synchronize()
+    assert np.abs(qad_host - ref_qad[:9]).max() <= 1e-14 * np.abs(ref_qad).max()
