@@ -391,6 +391,30 @@ def test_local_frame_statics_direct_solve(sri_lib, make_oracle, torch_mod, N):
     assert rel_err(lam0, o.wrench_local_solve(K[:5], ref0["Q"], F[:5], Mt[:5])) <= TOL
 
 
+@pytest.mark.parametrize("scale", [0.0, 6.0, 40.0])
+def test_local_frame_statics_pivot_patterns(sri_lib, make_oracle, torch_mod, scale):
+    """The blocked LU of the local-frame statics under different pivot patterns: K = 0 (the operator is D_TT (x) I3, every
+    pivot comes from far below the diagonal), moderate and large curvatures (pivots from inside the 4-column panel, chains of
+    exchanges).  Same pivot choice as the oracle's sequential LU, so the results agree to round-off times the conditioning."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    N, B = 16, 150
+    o = make_oracle(N)
+    rng = np.random.default_rng(int(scale) + 3)
+    K = scale * rng.uniform(-1, 1, size=(B, 3, 1)) * (1 + 0.3 * rng.normal(size=(B, 3, N)))
+    F = rng.uniform(-1, 1, size=(B, 3)); Mt = rng.uniform(-1, 1, size=(B, 3))
+    Q = rng.normal(size=(B, 4, N - 1)); Q /= np.linalg.norm(Q, axis=1, keepdims=True)   # any unit quaternions: the solve only rotates the loads with them
+    fbar = rng.normal(size=(B, 3, N)); lbar = rng.normal(size=(B, 3, N))
+    lam_ref = o.wrench_local_solve(K, Q, F, Mt, fbar=fbar, lbar=lbar)
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    with SpectralRodIntegrator(N, 0) as h:
+        info = torch_mod.full((B,), -1, dtype=torch_mod.int32, device="cuda")
+        lam = h.integrate_wrench_local(t(K), t(Q), t(F), t(Mt), fbar=t(fbar), lbar=t(lbar), info=info)
+        h.synchronize()
+    assert (info.cpu().numpy() == 0).all()
+    err = np.abs(lam.cpu().numpy() - lam_ref).reshape(B, -1).max(axis=1) / np.abs(lam_ref).reshape(B, -1).max(axis=1)
+    assert err.max() <= (TOL if scale <= 6.0 else 1e-10), err.max()
+
+
 def test_local_frame_statics_non_finite_rod_is_reported(sri_lib, make_oracle, torch_mod):
     """A rod with NaN / Inf curvature samples is flagged through info[] (non-finite pivot) and leaves its neighbours alone."""
     from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
