@@ -39,6 +39,17 @@ class RodBatch(ctypes.Structure):
     ]
 
 
+class NewtonReport(ctypes.Structure):
+    """struct sri_newton_report (include/sri.h)."""
+
+    _fields_ = [
+        ("iterations", c_int), ("converged", c_int), ("integrations", c_int64),
+        ("rms", c_double), ("max_abs", c_double), ("rms_history", c_double * 64), ("history_len", c_int),
+    ]
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, POINTER(c_double), c_void_p)  # sri_allreduce_fn
+
 # every symbol include/sri.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sri_chebyshev_points": (c_int, [c_int, c_double, c_void_p]),
@@ -65,6 +76,8 @@ SYMBOLS = {
     "sri_galerkin_residual": (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 9),
     "sri_generalised_forces": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "sri_solve_small_batched": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sri_newton_static_shape": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                        c_int, c_double, c_int64, ALLREDUCE_FN, c_void_p, POINTER(NewtonReport)]),
     "sri_generate_rods": (c_int, [c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_last_error_string": (c_char_p, []),
     "sri_kernel_launch_count": (c_int64, []),

@@ -319,6 +319,41 @@ class SpectralRodIntegrator:
         _lib.check(self._lib.sri_generalised_forces(self._h, batch, int(ne), _ptr(Lambda, "Lambda"), _ptr(out, "Qad")), "sri_generalised_forces")
         return out
 
+    def newton_static_shape(self, F_tip, M_tip, ne: int, H_diag=(1.0, 1.0, 0.77), qe=None, K0=None, tol: float = 1e-10,
+                            max_iter: int = 30, fd_step: float = 1e-6, total_dof: int = 0, allreduce=None):
+        """sri_newton_static_shape: the Newton loop of the static shape problem inside the library.  qe (in/out, zeros when
+        omitted) [batch][3*ne]; allreduce(norms) -- optional callable that replaces the 2-element float64 numpy array
+        [sum g^2, max |g|] by its reduction over the ranks.  Returns (qe, dict report)."""
+        self._follow_torch(F_tip)
+        batch = F_tip.shape[0]
+        if qe is None:
+            qe = _empty_like_kind(F_tip, (batch, 3 * int(ne)))
+            if isinstance(qe, np.ndarray):
+                qe[...] = 0.0
+            else:
+                qe.zero_()
+        H = np.ascontiguousarray(np.asarray(H_diag, dtype=np.float64))
+        rep = _lib.NewtonReport()
+        failure = []
+
+        def _cb(ptr, _ctx):
+            try:
+                allreduce(np.ctypeslib.as_array(ptr, shape=(2,)))
+                return 0
+            except Exception as exc:  # never unwind through the C frames
+                failure.append(exc)
+                return 1
+
+        cb = _lib.ALLREDUCE_FN(_cb) if allreduce is not None else _lib.ALLREDUCE_FN()
+        rc = self._lib.sri_newton_static_shape(self._h, batch, int(ne), H.ctypes.data, _ptr(F_tip, "F_tip"), _ptr(M_tip, "M_tip"),
+                                               _ptr(K0, "K0"), _ptr(qe, "qe"), float(tol), int(max_iter), float(fd_step),
+                                               int(total_dof), cb, None, ctypes.byref(rep))
+        if failure:
+            raise failure[0]
+        _lib.check(rc, "sri_newton_static_shape")
+        return qe, {"iterations": rep.iterations, "converged": bool(rep.converged), "integrations": rep.integrations,
+                    "rms": rep.rms, "max_abs": rep.max_abs, "rms_history": list(rep.rms_history[:rep.history_len])}
+
     def solve_small_batched(self, A, b, out=None, info=None):
         """A [batch][n][n] (row-major, destroyed), b [batch][n] -> x [batch][n]; CUDA tensors only."""
         self._follow_torch(A)

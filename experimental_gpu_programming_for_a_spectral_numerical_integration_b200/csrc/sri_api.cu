@@ -78,6 +78,11 @@ struct sri_context {
     double dmma_growth = sri::kDmmaGrowthDefault;
     bool use_dmma = false;
     bool wrench_configured = false, solve_small_configured = false;
+    struct NewtonWorkspace {  // buffers of sri_newton_static_shape, kept for the next call of the same shape
+        int64_t B = -1; int ne = 0; bool has_K0 = false;
+        double* block = nullptr;
+        double *K, *Q, *m, *g0, *J, *delta, *qe, *red, *F, *Mt, *K0, *qw, *Kw, *Qw, *mw, *gw, *Fw, *Mtw, *K0w;
+    } newton;
     double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
     size_t partial_cap = 0;
     unsigned* d_counter = nullptr;
@@ -428,6 +433,34 @@ __global__ void __launch_bounds__(256, 4) galerkin_residual_kernel(long long bat
         }
         if (lane == 0) { red[0] = a; red[1] = z; *counter = 0u; }
     }
+}
+
+// ---- Newton driver helpers (sri_newton_static_shape) ---------------------------------------------------------------
+// qw[d][b][j] = qe[b][j] + (j == d ? step : 0): the n forward-difference copies of the batch
+__global__ void fd_perturb_kernel(long long B, int n, double step, const double* __restrict__ qe, double* __restrict__ qw) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = B * n;
+    if (idx >= per * n) return;
+    const int d = (int)(idx / per);
+    const long long bj = idx - d * per;
+    const int j = (int)(bj % n);
+    const double v = qe[bj];
+    qw[idx] = (j == d) ? v + step : v;
+}
+
+// J[b][i][d] = (gw[d][b][i] - g0[b][i]) / step
+__global__ void fd_jacobian_kernel(long long B, int n, double step, const double* __restrict__ gw,
+                                   const double* __restrict__ g0, double* __restrict__ J) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * n * n) return;
+    const int d = (int)(idx % n);
+    const long long bi = idx / n;  // b * n + i
+    J[idx] = (gw[(long long)d * B * n + bi] - g0[bi]) / step;
+}
+
+__global__ void newton_update_kernel(long long total, double* __restrict__ qe, const double* __restrict__ delta) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) qe[idx] -= delta[idx];
 }
 
 // One thread per system: Gaussian elimination with partial pivoting.  The block's systems (contiguous in global memory)
@@ -1123,6 +1156,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_ptab) cudaFree(h->d_ptab);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_counter) cudaFree(h->d_counter);
+    if (h->newton.block) cudaFree(h->newton.block);
     for (int sl = 0; sl < 4; ++sl)
         if (h->d_list[sl]) cudaFree(h->d_list[sl]);
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) {
@@ -1485,6 +1519,101 @@ int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const
     solve_small_kernel<<<(unsigned)((batch + T - 1) / T), T, smem, h->stream>>>(batch, n, A, b, x, info);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+// Newton iteration of the static shape problem, host loop in this library (no torch, no Python in the loop): per iteration
+// one hot-path call on the 3 ne forward-difference copies of the batch, the fused Galerkin residual, the per-rod solve
+// and one 16-byte read of the norms.  rod_modeling.pdf section 2.2; BASELINE configs[4].
+int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* F_tip,
+                            const double* M_tip, const double* K0, double* qe, double tol, int max_iter, double fd_step,
+                            int64_t total_dof, sri_allreduce_fn reduce, void* reduce_ctx, sri_newton_report* report) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || max_iter < 0 || max_iter > 62 || !(fd_step > 0.0) ||
+        (batch > 0 && (!F_tip || !M_tip || !qe)))
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: bad arguments (1 <= ne <= 8, 0 <= max_iter <= 62, fd_step > 0)");
+    const int N = h->N, M = h->M, n = 3 * ne;
+    const int64_t B = batch, W = (int64_t)n * B;
+    double H[3];
+    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
+    else std::memcpy(H, H_diag, sizeof(H));
+    auto& ws = h->newton;
+    if (B > 0 && (ws.B != B || ws.ne != ne || ws.has_K0 != (K0 != nullptr))) {
+        SRI_CUDA(cudaStreamSynchronize(h->stream));
+        if (ws.block) SRI_CUDA(cudaFree(ws.block));
+        ws.block = nullptr; ws.B = -1;
+        const bool k0 = K0 != nullptr;
+        auto up = [](size_t v) { return (v + 1) & ~(size_t)1; };  // 16-byte aligned pieces
+        const size_t sz[] = {up((size_t)3 * N * B), up((size_t)4 * M * B), up((size_t)3 * M * B), up((size_t)n * B), up((size_t)n * n * B),
+                             up((size_t)n * B), up((size_t)n * B), 8, up((size_t)3 * B), up((size_t)3 * B), k0 ? up((size_t)3 * N * B) : 0,
+                             up((size_t)n * W), up((size_t)3 * N * W), up((size_t)4 * M * W), up((size_t)3 * M * W), up((size_t)n * W),
+                             up((size_t)3 * W), up((size_t)3 * W), k0 ? up((size_t)3 * N * W) : 0};
+        size_t total = 0;
+        for (size_t v : sz) total += v;
+        SRI_CUDA(cudaMalloc(&ws.block, total * sizeof(double)));
+        double** fields[] = {&ws.K, &ws.Q, &ws.m, &ws.g0, &ws.J, &ws.delta, &ws.qe, &ws.red, &ws.F, &ws.Mt, &ws.K0,
+                             &ws.qw, &ws.Kw, &ws.Qw, &ws.mw, &ws.gw, &ws.Fw, &ws.Mtw, &ws.K0w};
+        size_t off = 0;
+        for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) { *fields[i] = sz[i] ? ws.block + off : nullptr; off += sz[i]; }
+        ws.B = B; ws.ne = ne; ws.has_K0 = k0;
+    }
+    cudaStream_t st = h->stream;
+    if (B > 0) {
+        SRI_CUDA(cudaMemcpyAsync(ws.qe, qe, sizeof(double) * n * B, cudaMemcpyDefault, st));
+        SRI_CUDA(cudaMemcpyAsync(ws.F, F_tip, sizeof(double) * 3 * B, cudaMemcpyDefault, st));
+        SRI_CUDA(cudaMemcpyAsync(ws.Mt, M_tip, sizeof(double) * 3 * B, cudaMemcpyDefault, st));
+        if (K0) SRI_CUDA(cudaMemcpyAsync(ws.K0, K0, sizeof(double) * 3 * N * B, cudaMemcpyDefault, st));
+        for (int d = 0; d < n; ++d) {  // tip loads (and K0) of the forward-difference copies
+            SRI_CUDA(cudaMemcpyAsync(ws.Fw + (size_t)d * 3 * B, ws.F, sizeof(double) * 3 * B, cudaMemcpyDeviceToDevice, st));
+            SRI_CUDA(cudaMemcpyAsync(ws.Mtw + (size_t)d * 3 * B, ws.Mt, sizeof(double) * 3 * B, cudaMemcpyDeviceToDevice, st));
+            if (K0) SRI_CUDA(cudaMemcpyAsync(ws.K0w + (size_t)d * 3 * N * B, ws.K0, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    auto evaluate = [&](int64_t rods, const double* q, double* K, double* Q, double* m, const double* F, const double* Mt,
+                        const double* k0, double* g, double* red) -> int {
+        SRI_TRY(sri_strain_from_modes(h, rods, ne, q, K));
+        sri_rod_batch rb{};
+        rb.batch = rods; rb.K = K; rb.F_tip = F; rb.M_tip = Mt; rb.Q = Q; rb.m = m;
+        SRI_TRY(sri_integrate_all(h, &rb));
+        return sri_galerkin_residual(h, rods, ne, K, k0, H, Q, nullptr, m, Mt, g, red);
+    };
+    sri_newton_report rep{};
+    const double dof = (double)(total_dof > 0 ? total_dof : (int64_t)n * B);
+    if (B > 0) SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red));
+    rep.integrations = 1;
+    for (int it = 0;; ++it) {
+        double red[2] = {0.0, 0.0};
+        if (B > 0) {
+            SRI_CUDA(cudaMemcpyAsync(red, ws.red, sizeof(red), cudaMemcpyDeviceToHost, st));
+            SRI_CUDA(cudaStreamSynchronize(st));
+        }
+        if (reduce && reduce(red, reduce_ctx) != 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: the reduction callback failed");
+        rep.rms = dof > 0 ? std::sqrt(red[0] / dof) : 0.0;
+        rep.max_abs = red[1];
+        rep.rms_history[rep.history_len++] = rep.rms;
+        if (rep.rms < tol) { rep.converged = 1; break; }
+        if (it == max_iter) break;
+        if (B > 0) {
+            const long long tq = (long long)n * W, tj = (long long)B * n * n, tu = (long long)n * B;
+            fd_perturb_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.qe, ws.qw);
+            g_launches.fetch_add(1);
+            SRI_TRY(evaluate(W, ws.qw, ws.Kw, ws.Qw, ws.mw, ws.Fw, ws.Mtw, ws.K0w, ws.gw, nullptr));
+            fd_jacobian_kernel<<<(unsigned)((tj + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.gw, ws.g0, ws.J);
+            g_launches.fetch_add(1);
+            SRI_TRY(sri_solve_small_batched(h, B, n, ws.J, ws.g0, ws.delta, nullptr));
+            newton_update_kernel<<<(unsigned)((tu + 255) / 256), 256, 0, st>>>(tu, ws.qe, ws.delta);
+            g_launches.fetch_add(1);
+            SRI_CUDA(cudaGetLastError());
+            SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red));
+        }
+        rep.iterations += 1;
+        rep.integrations += n + 1;
+    }
+    if (B > 0) {
+        SRI_CUDA(cudaMemcpyAsync(qe, ws.qe, sizeof(double) * n * B, cudaMemcpyDefault, st));
+        SRI_CUDA(cudaStreamSynchronize(st));
+    }
+    if (report) *report = rep;
     return SRI_OK;
 }
 

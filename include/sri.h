@@ -174,6 +174,27 @@ int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, 
                           const double* Q, const double* q0, const double* m, const double* M_tip, double* g,
                           double* norm2_and_max);
 
+/* Newton iteration of the static shape problem (BASELINE configs[4]; rod_modeling.pdf section 2.2), the loop inside the
+ * library: unknowns qe [batch][3*ne] (modal strain coordinates, in: initial guess, out: solution; device or host pointer),
+ * residual g = sri_galerkin_residual of the four-stage integration of K = Phi qe under (F_tip, M_tip), forward-difference
+ * Jacobian (the 3*ne perturbed copies of the batch go through ONE sri_integrate_all), per-rod solve, update; stops when
+ * sqrt(sum g^2 / total_dof) < tol or after max_iter iterations (<= 62).  total_dof: number of unknowns over all ranks
+ * (0 => batch*3*ne).  reduce (or NULL): called once per iteration with the 2 host doubles [sum g^2, max |g|] of this
+ * rank's rods, must replace them by the sum / max over the ranks (e.g. MPI_Allreduce, ncclAllReduce + copy) and return 0
+ * -- the only collective of the method; every rank must call with the same max_iter, also ranks with batch == 0. */
+typedef int (*sri_allreduce_fn)(double* norm2_and_max, void* ctx);
+typedef struct sri_newton_report {
+    int iterations;        /* Newton updates taken */
+    int converged;         /* 1 when the tolerance was met */
+    int64_t integrations;  /* four-stage integrations of the batch: 1 + iterations * (3*ne + 1) */
+    double rms, max_abs;   /* of the last residual, over all ranks */
+    double rms_history[64];
+    int history_len;
+} sri_newton_report;
+int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* F_tip,
+                            const double* M_tip, const double* K0, double* qe, double tol, int max_iter, double fd_step,
+                            int64_t total_dof, sri_allreduce_fn reduce, void* reduce_ctx, sri_newton_report* report);
+
 /* Batched dense solve A x = b for small systems (n <= 24), partial pivoting, one rod per thread: the Newton step
  * of the static shape problem.  A [batch][n][n] row-major (may be overwritten), b [batch][n] -> x [batch][n].
  * info [batch] or NULL as in sri_integrate_quaternions.  Device pointers only. */

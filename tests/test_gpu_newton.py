@@ -232,3 +232,40 @@ def test_generalised_forces_close_the_static_balance(h16, oracle16, torch_mod):
     qad_host = h16.generalised_forces(lam_np[:9], ne)
     h16.synchronize()
     assert np.abs(qad_host - ref_qad[:9]).max() <= 1e-14 * np.abs(ref_qad).max()
+
+
+def test_native_newton_driver_matches_the_python_driver(h16, torch_mod):
+    """sri_newton_static_shape (the loop inside the C ABI) takes the same steps as newton.StaticShapeSolver: same iteration
+    count, same residual history and solution to round-off; device and host buffers; K0; the reduction callback."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200.newton import StaticShapeSolver
+    B, ne = 417, 3
+    rng = np.random.default_rng(21)
+    F = np.zeros((B, 3)); F[:, 2] = -rng.uniform(0.1, 2.0, size=B)
+    Mt = rng.uniform(-0.1, 0.1, size=(B, 3))
+    K0 = 0.2 * rng.normal(size=(B, 3, 1)) * np.ones((1, 1, 16))
+    tF, tM, tK0 = (torch_mod.from_numpy(np.ascontiguousarray(a)).cuda() for a in (F, Mt, K0))
+    H = (1.0, 1.0, 0.77)
+    for k0_t, k0_h in ((None, None), (tK0, K0)):
+        q_py, rep_py = StaticShapeSolver(h16, H, ne=ne).solve(tF, tM, K0=k0_t, use_graph=False)
+        q_c, rep_c = h16.newton_static_shape(tF, tM, ne, H, K0=k0_t)
+        h16.synchronize()
+        assert rep_c["converged"] and rep_c["iterations"] == rep_py.iterations and rep_c["integrations"] == rep_py.integrations
+        # (torch divides by the step through a reciprocal: the forward differences agree to ~1e-10, not to the bit)
+        big = [i for i, v in enumerate(rep_py.rms_history) if v > 1e-6]
+        assert np.allclose(np.array(rep_c["rms_history"])[big], np.array(rep_py.rms_history)[big], rtol=1e-6)
+        assert np.abs(q_c.cpu().numpy() - q_py.cpu().numpy()).max() <= 1e-11
+        q_h, rep_h = h16.newton_static_shape(F, Mt, ne, H, K0=k0_h)          # host buffers
+        assert rep_h["iterations"] == rep_c["iterations"] and np.abs(q_h - q_c.cpu().numpy()).max() <= 1e-15
+    # the reduction callback sees this rank's norms and may replace them (two identical ranks: sum doubles, max stays)
+    seen = []
+    def two_ranks(norms):
+        seen.append(norms.copy()); norms[0] *= 2.0
+    q_r, rep_r = h16.newton_static_shape(tF, tM, ne, H, total_dof=2 * B * 3 * ne, allreduce=two_ranks)
+    assert rep_r["converged"] and len(seen) == rep_r["iterations"] + 1
+    q_1, rep_1 = h16.newton_static_shape(tF, tM, ne, H)
+    assert np.allclose(rep_r["rms_history"], rep_1["rms_history"], rtol=1e-12) and torch_mod.equal(q_r, q_1)
+    # an empty shard still takes part in every reduction
+    calls = []
+    empty = torch_mod.zeros((0, 3), dtype=torch_mod.float64, device="cuda")
+    _, rep_e = h16.newton_static_shape(empty, empty, ne, H, total_dof=10, max_iter=3, allreduce=lambda nrm: (calls.append(1), nrm.__setitem__(0, 1.0)))
+    assert not rep_e["converged"] and rep_e["iterations"] == 3 and len(calls) == 4

@@ -18,6 +18,7 @@ ap.add_argument("--rods", type=int, default=100000)
 ap.add_argument("--ne", type=int, default=3)
 ap.add_argument("--N", type=int, default=16)
 ap.add_argument("--jacobian", default="batched", choices=("batched", "columns"))
+ap.add_argument("--driver", default="python", choices=("python", "native"), help="newton.py (torch + CUDA graph) or sri_newton_static_shape (loop inside the C ABI)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -33,27 +34,42 @@ F = torch.empty((B, 3), dtype=torch.float64, device=dev)
 h.generate_rods(0x5EED, lo, B, None, F, None, None)
 F[:, 2] = -(F[:, 2] + 1.0); F[:, :2] = 0.0
 Mt = torch.zeros((B, 3), dtype=torch.float64, device=dev)
-solver = StaticShapeSolver(h, (1.0, 1.0, 0.77), ne=args.ne, jacobian=args.jacobian)
-# first solve of this shape: runs one iteration eagerly, captures the iteration into a CUDA graph, replays it (every rank
-# takes part, so the collectives match); the timed solve below replays the cached graph from its first iteration on
+from types import SimpleNamespace
+from experimental_gpu_programming_for_a_spectral_numerical_integration_b200.sharding import allreduce_residual
+if args.driver == "native":
+    total_dof = args.rods * 3 * args.ne
+    def _allreduce(norms):  # the one collective of the method: 16 bytes per iteration
+        t = torch.from_numpy(norms.copy()).to(dev)
+        allreduce_residual(t)
+        norms[:] = t.cpu().numpy()
+    def solve(use_graph=True):
+        qe, rep = h.newton_static_shape(F, Mt, args.ne, (1.0, 1.0, 0.77), tol=1e-10, max_iter=30, total_dof=total_dof,
+                                        allreduce=_allreduce if world > 1 else None)
+        return qe, SimpleNamespace(**rep)
+else:
+    solver = StaticShapeSolver(h, (1.0, 1.0, 0.77), ne=args.ne, jacobian=args.jacobian)
+    def solve(use_graph=True):
+        return solver.solve(F, Mt, tol=1e-10, max_iter=30, use_graph=use_graph)
+# first solve of this shape (python driver: runs one iteration eagerly, captures the iteration into a CUDA graph, replays it;
+# native driver: allocates the workspace); the timed solve below reuses what the first one set up
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-solver.solve(F, Mt, tol=1e-10, max_iter=30)
+solve()
 torch.cuda.synchronize()
 first = time.perf_counter() - t0
 t0 = time.perf_counter()
-solver.solve(F, Mt, tol=1e-10, max_iter=30, use_graph=False)
+solve(use_graph=False)
 torch.cuda.synchronize()
 eager = time.perf_counter() - t0
 if world > 1: dist.barrier()
 l0 = kernel_launch_count()
 t0 = time.perf_counter()
-qe, rep = solver.solve(F, Mt, tol=1e-10, max_iter=30)
+qe, rep = solve()
 torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
 if world > 1: dist.all_reduce(dt, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"config": "cfg5 Newton static shape", "rods_total": args.rods, "n_gpus": world, "N": args.N, "ne": args.ne, "jacobian": args.jacobian,
+    print(json.dumps({"config": "cfg5 Newton static shape", "rods_total": args.rods, "n_gpus": world, "N": args.N, "ne": args.ne, "jacobian": args.jacobian, "driver": args.driver,
                       "converged": rep.converged, "newton_iterations": rep.iterations, "integrations_of_the_batch": rep.integrations,
                       "seconds": float(dt.item()), "seconds_eager_launches": eager, "seconds_first_solve_with_capture": first, "rod_solves_per_s": args.rods / float(dt.item()),
                       "rod_integrations_per_s": args.rods * rep.integrations / float(dt.item()),
