@@ -269,3 +269,17 @@ def test_native_newton_driver_matches_the_python_driver(h16, torch_mod):
     empty = torch_mod.zeros((0, 3), dtype=torch_mod.float64, device="cuda")
     _, rep_e = h16.newton_static_shape(empty, empty, ne, H, total_dof=10, max_iter=3, allreduce=lambda nrm: (calls.append(1), nrm.__setitem__(0, 1.0)))
     assert not rep_e["converged"] and rep_e["iterations"] == 3 and len(calls) == 4
+
+
+def test_cpp_host_drives_the_newton_solve(sri_lib):
+    """examples/newton_main.cpp: C++ host code -> sri_newton_static_shape; pure tip moments must give K = H^-1 M_tip."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "examples" / "newton_main_gpu"
+    if not exe.exists():
+        import __graft_entry__ as g
+        g._build_cpp_example(root / "experimental_gpu_programming_for_a_spectral_numerical_integration_b200" / "libsri_cuda.so")
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.startswith("converged 1")
