@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kerne
             t0 = __shfl_sync(FULL, ys, src); t1 = __shfl_sync(FULL, ys, src + 1);
             t2 = __shfl_sync(FULL, ys, src + 2); t3 = __shfl_sync(FULL, ys, src + 3);
         };
+        // a row inside the block [c0, c0 + 4) takes the block's solved value: its offset is row & 3 = lane & 3 for both
+        // rows of a lane (c0 and 32 are multiples of 4), so the selection is made once per block with loop-invariant predicates
+        const int l3 = lane & 3;
         auto row_update = [&](int row, int c0, bool beyond, double t0, double t1, double t2, double t3, double& y) {
             const int d = row - c0;
             if (beyond) {
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(32 * kWrenchWarps, 1) wrench_local_solve_kerne
                 const double2 lb = *reinterpret_cast<const double2*>(A + row * LD + c0 + 2);
                 y = fma(-lb.y, t3, fma(-lb.x, t2, fma(-la.y, t1, fma(-la.x, t0, y))));
             } else if (d >= 0 && d < 4) {
-                y = d == 0 ? t0 : (d == 1 ? t1 : (d == 2 ? t2 : t3));
+                y = l3 == 0 ? t0 : (l3 == 1 ? t1 : (l3 == 2 ? t2 : t3));
             }
         };
         auto lower4 = [&](int c0, double t0, double& t1, double& t2, double& t3) {  // unit lower 4 x 4 triangle
