@@ -391,3 +391,37 @@ def test_generator_is_sharding_invariant_and_in_range(oracle16):
     assert (fb[:, 2] <= 0).all() and (fb[:, 2] >= -1).all() and not fb[:, :2].any()
     t = 2 * oracle16.chebyshev_points() - 1                       # K_c is constant + linear in X
     assert np.abs(K[:, :, 0] + K[:, :, -1] - 2 * K[:, :, 5] + (K[:, :, 0] - K[:, :, -1]) * t[5]).max() < 1e-14
+
+
+def test_analytic_jacobian_of_the_discrete_static_shape_residual(oracle16):
+    """oracle/tangent.py: the exact tangent of the discrete four-stage map (stage-1 operator shared by all directions) gives
+    the Newton Jacobian of the Galerkin residual; pinned here against central differences of the oracle's own residual
+    (with and without a reference curvature K0).  Groundwork for the multi-right-hand-side elimination of DESIGN section 7."""
+    from numpy.polynomial import legendre as L
+    from oracle.tangent import cc_weights, galerkin_residual_and_jacobian
+    o = oracle16
+    B, ne = 3, 3
+    n = 3 * ne
+    rng = np.random.default_rng(0)
+    qe = 0.8 * rng.normal(size=(B, n))
+    F = rng.uniform(-1, 1, size=(B, 3)); Mt = rng.uniform(-0.5, 0.5, size=(B, 3))
+    K0 = 0.2 * rng.normal(size=(B, 3, 16))
+    H = np.array([1.0, 0.9, 0.77])
+    x = o.chebyshev_points(); w = cc_weights(16)
+    P = np.stack([L.legval(2 * x - 1, [0] * k + [1]) for k in range(ne)])
+
+    for k0 in (None, K0):
+        def g_of(q):
+            K = o.strain_from_modes(q, ne)
+            out = o.integrate_all(K, F, Mt, explicit_inverse=False, want=("Q", "m", "n"))
+            rho = o.shape_residual(K, H, out["Q"], out["m"], Mt, K0=k0)
+            return np.einsum("bci,ki,i->bck", rho, P, w).reshape(B, n)
+
+        g, J = galerkin_residual_and_jacobian(o, qe, F, Mt, H, ne, K0=k0)
+        assert np.abs(g - g_of(qe)).max() <= 1e-14
+        Jfd = np.empty_like(J)
+        h = 1e-6
+        for d in range(n):
+            e = np.zeros(n); e[d] = h
+            Jfd[:, :, d] = (g_of(qe + e) - g_of(qe - e)) / (2 * h)
+        assert np.abs(J - Jfd).max() <= 1e-8 * np.abs(Jfd).max()
