@@ -56,6 +56,17 @@ def test_argument_errors_are_reported_not_thrown(sri_lib):
     assert sri_lib.sri_create(65, 0, ctypes.byref(h)) == -2 and not h
     assert sri_lib.sri_create(16, 0, None) == -1
     assert sri_lib.sri_destroy(None) == 0
+    # every entry point that takes a handle rejects a null handle with a status, also the ones added for the static shape
+    # problem (no compute is attempted)
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import _lib
+    H = (ctypes.c_double * 3)(1.0, 1.0, 0.77)
+    rep = _lib.NewtonReport()
+    assert sri_lib.sri_newton_static_shape(None, 0, 3, H, None, None, None, None, 1e-10, 30, 1e-6, 0, _lib.ALLREDUCE_FN(), None,
+                                           ctypes.byref(rep)) == -1
+    assert sri_lib.sri_galerkin_residual(None, 0, 3, None, None, H, None, None, None, None, None, None) == -1
+    assert sri_lib.sri_generalised_forces(None, 0, 3, None, None) == -1
+    assert sri_lib.sri_integrate_wrench_local(None, 0, None, None, None, None, None, None, None, None, None, None) == -1
+    assert b"handle" in sri_lib.sri_last_error_string().lower()
 
 
 @pytest.mark.skipif(HAS_CUDA, reason="checks the no-GPU failure mode")
