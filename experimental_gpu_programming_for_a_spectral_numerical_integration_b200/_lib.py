@@ -75,6 +75,7 @@ SYMBOLS = {
     "sri_project_onto_modes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "sri_galerkin_residual": (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 9),
     "sri_generalised_forces": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "sri_shape_jacobian": (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 8),
     "sri_solve_small_batched": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_newton_static_shape": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                         c_int, c_double, c_int64, ALLREDUCE_FN, c_void_p, POINTER(NewtonReport)]),

@@ -319,6 +319,20 @@ class SpectralRodIntegrator:
         _lib.check(self._lib.sri_generalised_forces(self._h, batch, int(ne), _ptr(Lambda, "Lambda"), _ptr(out, "Qad")), "sri_generalised_forces")
         return out
 
+    def shape_jacobian(self, Q, n, m, M_tip, ne: int, H_diag, q0=None, Gamma=None, out=None):
+        """J[b][j][d] = d g_j / d qe_d of galerkin_residual, analytic and solve-free (sri_shape_jacobian); Q, n, m are the
+        stage outputs at the current qe."""
+        self._follow_torch(Q)
+        batch = Q.shape[0]
+        H = np.ascontiguousarray(np.asarray(H_diag, dtype=np.float64))
+        nq = 3 * int(ne)
+        if out is None:
+            out = _empty_like_kind(Q, (batch, nq, nq))
+        _lib.check(self._lib.sri_shape_jacobian(self._h, batch, int(ne), H.ctypes.data, _ptr(Q, "Q"), _ptr(q0, "q0"),
+                                                _ptr(Gamma, "Gamma"), _ptr(n, "n"), _ptr(m, "m"), _ptr(M_tip, "M_tip"),
+                                                _ptr(out, "J")), "sri_shape_jacobian")
+        return out
+
     def newton_static_shape(self, F_tip, M_tip, ne: int, H_diag=(1.0, 1.0, 0.77), qe=None, K0=None, tol: float = 1e-10,
                             max_iter: int = 30, fd_step: float = 1e-6, total_dof: int = 0, allreduce=None):
         """sri_newton_static_shape: the Newton loop of the static shape problem inside the library.  qe (in/out, zeros when

@@ -72,6 +72,8 @@ struct sri_context {
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
     double* d_ptab = nullptr;    // Legendre polynomials at the nodes, P_k(2 x_i - 1), [8][N]
+    double* d_jac = nullptr;     // S = Dn_NN^-1 and S_T = D_TT^-1, row-major [M][M] each (sri_shape_jacobian), built on first use
+    bool jac_configured = false;
     int fused_blocks_per_sm = 0;
     int stage_blocks_per_sm = 0;
     int dmma_blocks_per_sm = 0;
@@ -79,9 +81,9 @@ struct sri_context {
     bool use_dmma = false;
     bool wrench_configured = false, solve_small_configured = false;
     struct NewtonWorkspace {  // buffers of sri_newton_static_shape, kept for the next call of the same shape
-        int64_t B = -1; int ne = 0; bool has_K0 = false;
+        int64_t B = -1; int ne = 0; bool has_K0 = false, analytic = false;
         double* block = nullptr;
-        double *K, *Q, *m, *g0, *J, *delta, *qe, *red, *F, *Mt, *K0, *qw, *Kw, *Qw, *mw, *gw, *Fw, *Mtw, *K0w;
+        double *K, *Q, *m, *nn, *g0, *J, *delta, *qe, *red, *F, *Mt, *K0, *qw, *Kw, *Qw, *mw, *gw, *Fw, *Mtw, *K0w;
     } newton;
     double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
     size_t partial_cap = 0;
@@ -754,6 +756,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_reduce) cudaFree(h->d_reduce);
     if (h->d_ccw) cudaFree(h->d_ccw);
     if (h->d_ptab) cudaFree(h->d_ptab);
+    if (h->d_jac) cudaFree(h->d_jac);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->newton.block) cudaFree(h->newton.block);
@@ -1104,6 +1107,49 @@ int sri_generalised_forces(sri_handle h, int64_t batch, int ne, const double* La
     return st.finish();
 }
 
+int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* Q, const double* q0,
+                       const double* Gamma, const double* n, const double* m, const double* M_tip, double* J) {
+    SRI_TRY(check_handle(h));
+    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || (batch > 0 && (!Q || !n || !m || !M_tip || !J)))
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_shape_jacobian: bad arguments (1 <= ne <= 8)");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M, nq = 3 * ne;
+    double H[3];
+    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
+    else std::memcpy(H, H_diag, sizeof(H));
+    if (!h->d_jac) {
+        std::vector<double> t((size_t)2 * M * M);
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) {
+                t[(size_t)i * M + j] = h->ops.S[(size_t)j * M + i];
+                t[(size_t)M * M + (size_t)i * M + j] = h->ops.ST[(size_t)j * M + i];
+            }
+        SRI_CUDA(cudaMalloc(&h->d_jac, t.size() * sizeof(double)));
+        SRI_CUDA(cudaMemcpy(h->d_jac, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    constexpr int kWarps = 4;
+    const size_t smem = ((size_t)2 * M * M + (size_t)kWarps * JacobianScratch::total(N)) * sizeof(double);
+    if (!h->jac_configured) {
+        if (smem > 48 * 1024) SRI_CUDA(cudaFuncSetAttribute(shape_jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->jac_configured = true;
+    }
+    Staging st(h);
+    const double *dQ, *dq0, *dG, *dn, *dm, *dMt; double* dJ;
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &dq0));
+    SRI_TRY(st.in(Gamma, (size_t)batch * 3 * N, &dG));
+    SRI_TRY(st.in(n, (size_t)batch * 3 * M, &dn));
+    SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
+    SRI_TRY(st.out(J, (size_t)batch * nq * nq, &dJ));
+    const long long want = (batch + kWarps - 1) / kWarps, cap = (long long)h->sm_count * 8;
+    shape_jacobian_kernel<<<(unsigned)(want < cap ? want : cap), 32 * kWarps, smem, h->stream>>>(
+        batch, N, ne, h->d_jac, h->d_jac + (size_t)M * M, h->d_ptab, h->d_ccw, H[0], H[1], H[2], dQ, dq0, dG, dn, dm, dMt, dJ);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return st.finish();
+}
+
 int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const double* b, double* x, int* info) {
     SRI_TRY(check_handle(h));
     if (batch < 0 || n < 1 || n > 24 || (batch > 0 && (!A || !b || !x))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: bad arguments (1 <= n <= 24)");
@@ -1129,33 +1175,35 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
                             const double* M_tip, const double* K0, double* qe, double tol, int max_iter, double fd_step,
                             int64_t total_dof, sri_allreduce_fn reduce, void* reduce_ctx, sri_newton_report* report) {
     SRI_TRY(check_handle(h));
-    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || max_iter < 0 || max_iter > 62 || !(fd_step > 0.0) ||
+    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || max_iter < 0 || max_iter > 62 || !(fd_step >= 0.0) ||
         (batch > 0 && (!F_tip || !M_tip || !qe)))
-        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: bad arguments (1 <= ne <= 8, 0 <= max_iter <= 62, fd_step > 0)");
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: bad arguments (1 <= ne <= 8, 0 <= max_iter <= 62, fd_step >= 0)");
+    const bool analytic = fd_step == 0.0;  // Jacobian from sri_shape_jacobian instead of forward differences
     const int N = h->N, M = h->M, n = 3 * ne;
-    const int64_t B = batch, W = (int64_t)n * B;
+    const int64_t B = batch, W = analytic ? 0 : (int64_t)n * B;
     double H[3];
     if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
     else std::memcpy(H, H_diag, sizeof(H));
     auto& ws = h->newton;
-    if (B > 0 && (ws.B != B || ws.ne != ne || ws.has_K0 != (K0 != nullptr))) {
+    if (B > 0 && (ws.B != B || ws.ne != ne || ws.has_K0 != (K0 != nullptr) || ws.analytic != analytic)) {
         SRI_CUDA(cudaStreamSynchronize(h->stream));
         if (ws.block) SRI_CUDA(cudaFree(ws.block));
         ws.block = nullptr; ws.B = -1;
         const bool k0 = K0 != nullptr;
         auto up = [](size_t v) { return (v + 1) & ~(size_t)1; };  // 16-byte aligned pieces
-        const size_t sz[] = {up((size_t)3 * N * B), up((size_t)4 * M * B), up((size_t)3 * M * B), up((size_t)n * B), up((size_t)n * n * B),
+        const size_t sz[] = {up((size_t)3 * N * B), up((size_t)4 * M * B), up((size_t)3 * M * B), up((size_t)3 * M * B), up((size_t)n * B), up((size_t)n * n * B),
                              up((size_t)n * B), up((size_t)n * B), 8, up((size_t)3 * B), up((size_t)3 * B), k0 ? up((size_t)3 * N * B) : 0,
                              up((size_t)n * W), up((size_t)3 * N * W), up((size_t)4 * M * W), up((size_t)3 * M * W), up((size_t)n * W),
                              up((size_t)3 * W), up((size_t)3 * W), k0 ? up((size_t)3 * N * W) : 0};
         size_t total = 0;
         for (size_t v : sz) total += v;
         SRI_CUDA(cudaMalloc(&ws.block, total * sizeof(double)));
-        double** fields[] = {&ws.K, &ws.Q, &ws.m, &ws.g0, &ws.J, &ws.delta, &ws.qe, &ws.red, &ws.F, &ws.Mt, &ws.K0,
+        double** fields[] = {&ws.K, &ws.Q, &ws.m, &ws.nn, &ws.g0, &ws.J, &ws.delta, &ws.qe, &ws.red, &ws.F, &ws.Mt, &ws.K0,
                              &ws.qw, &ws.Kw, &ws.Qw, &ws.mw, &ws.gw, &ws.Fw, &ws.Mtw, &ws.K0w};
+        static_assert(sizeof(sz) / sizeof(sz[0]) == sizeof(fields) / sizeof(fields[0]), "one size per workspace field");
         size_t off = 0;
         for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) { *fields[i] = sz[i] ? ws.block + off : nullptr; off += sz[i]; }
-        ws.B = B; ws.ne = ne; ws.has_K0 = k0;
+        ws.B = B; ws.ne = ne; ws.has_K0 = k0; ws.analytic = analytic;
     }
     cudaStream_t st = h->stream;
     if (B > 0) {
@@ -1163,23 +1211,24 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         SRI_CUDA(cudaMemcpyAsync(ws.F, F_tip, sizeof(double) * 3 * B, cudaMemcpyDefault, st));
         SRI_CUDA(cudaMemcpyAsync(ws.Mt, M_tip, sizeof(double) * 3 * B, cudaMemcpyDefault, st));
         if (K0) SRI_CUDA(cudaMemcpyAsync(ws.K0, K0, sizeof(double) * 3 * N * B, cudaMemcpyDefault, st));
-        for (int d = 0; d < n; ++d) {  // tip loads (and K0) of the forward-difference copies
+        for (int d = 0; d < n && !analytic; ++d) {  // tip loads (and K0) of the forward-difference copies
             SRI_CUDA(cudaMemcpyAsync(ws.Fw + (size_t)d * 3 * B, ws.F, sizeof(double) * 3 * B, cudaMemcpyDeviceToDevice, st));
             SRI_CUDA(cudaMemcpyAsync(ws.Mtw + (size_t)d * 3 * B, ws.Mt, sizeof(double) * 3 * B, cudaMemcpyDeviceToDevice, st));
             if (K0) SRI_CUDA(cudaMemcpyAsync(ws.K0w + (size_t)d * 3 * N * B, ws.K0, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToDevice, st));
         }
     }
     auto evaluate = [&](int64_t rods, const double* q, double* K, double* Q, double* m, const double* F, const double* Mt,
-                        const double* k0, double* g, double* red) -> int {
+                        const double* k0, double* g, double* red, double* nout = nullptr) -> int {
         SRI_TRY(sri_strain_from_modes(h, rods, ne, q, K));
         sri_rod_batch rb{};
-        rb.batch = rods; rb.K = K; rb.F_tip = F; rb.M_tip = Mt; rb.Q = Q; rb.m = m;
+        rb.batch = rods; rb.K = K; rb.F_tip = F; rb.M_tip = Mt; rb.Q = Q; rb.m = m; rb.n = nout;
         SRI_TRY(sri_integrate_all(h, &rb));
         return sri_galerkin_residual(h, rods, ne, K, k0, H, Q, nullptr, m, Mt, g, red);
     };
     sri_newton_report rep{};
     const double dof = (double)(total_dof > 0 ? total_dof : (int64_t)n * B);
-    if (B > 0) SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red));
+    double* nbase = analytic ? ws.nn : nullptr;
+    if (B > 0) SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, nbase));
     rep.integrations = 1;
     for (int it = 0;; ++it) {
         double red[2] = {0.0, 0.0};
@@ -1195,19 +1244,23 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         if (it == max_iter) break;
         if (B > 0) {
             const long long tq = (long long)n * W, tj = (long long)B * n * n, tu = (long long)n * B;
-            fd_perturb_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.qe, ws.qw);
-            g_launches.fetch_add(1);
-            SRI_TRY(evaluate(W, ws.qw, ws.Kw, ws.Qw, ws.mw, ws.Fw, ws.Mtw, ws.K0w, ws.gw, nullptr));
-            fd_jacobian_kernel<<<(unsigned)((tj + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.gw, ws.g0, ws.J);
-            g_launches.fetch_add(1);
+            if (analytic) {
+                SRI_TRY(sri_shape_jacobian(h, B, ne, H, ws.Q, nullptr, nullptr, ws.nn, ws.m, ws.Mt, ws.J));
+            } else {
+                fd_perturb_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.qe, ws.qw);
+                g_launches.fetch_add(1);
+                SRI_TRY(evaluate(W, ws.qw, ws.Kw, ws.Qw, ws.mw, ws.Fw, ws.Mtw, ws.K0w, ws.gw, nullptr));
+                fd_jacobian_kernel<<<(unsigned)((tj + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.gw, ws.g0, ws.J);
+                g_launches.fetch_add(1);
+            }
             SRI_TRY(sri_solve_small_batched(h, B, n, ws.J, ws.g0, ws.delta, nullptr));
             newton_update_kernel<<<(unsigned)((tu + 255) / 256), 256, 0, st>>>(tu, ws.qe, ws.delta);
             g_launches.fetch_add(1);
             SRI_CUDA(cudaGetLastError());
-            SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red));
+            SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, nbase));
         }
         rep.iterations += 1;
-        rep.integrations += n + 1;
+        rep.integrations += analytic ? 1 : n + 1;
     }
     if (B > 0) {
         SRI_CUDA(cudaMemcpyAsync(qe, ws.qe, sizeof(double) * n * B, cudaMemcpyDefault, st));

@@ -8,6 +8,7 @@
 
 #include "sri_device.cuh"
 #include "sri_stage_dmma.cuh"  // dmma_m8n8k4
+#include "sri_wrench_solve.cuh"  // quat_to_rot_rm
 
 namespace {
 
@@ -271,6 +272,111 @@ __global__ void __launch_bounds__(256, 4) galerkin_residual_kernel(long long bat
             z = fmax(z, __shfl_xor_sync(0xffffffffu, z, off));
         }
         if (lane == 0) { red[0] = a; red[1] = z; *counter = 0u; }
+    }
+}
+
+// ---- analytic Jacobian of the Galerkin residual (sri_shape_jacobian) ---------------------------------------------------
+// J[b][j'][d] = d g_j' / d qe_d without any linear solve: the variation of the rotation is left-trivialised,
+// dR = [dtheta]x R with dtheta' = R dK, dtheta(base) = 0, so a direction dK = P_k(t) e_c costs two contractions with the
+// cached integration matrices S = Dn_NN^-1 (base condition) and S_T = D_TT^-1 (tip condition):
+//     u_i = P_k(t_i) R_i[:, c]                  dtheta = S u                       (nodes 0..M-1; 0 at the base node)
+//     v_j = -((dtheta_j x b_j) x n_j)          dm     = S_T v                     (nodes 1..N-1; 0 at the tip node)
+//     drho_i = H dK_i - R_i^T (dm_i - dtheta_i x m_i),      dg = sum_i w_i P(t_i)^T drho_i.
+// One warp per rod; nodal data and the per-direction vectors in the warp's shared-memory scratch, S and S_T in the CTA's.
+struct JacobianScratch {  // doubles per warp, for N nodes
+    __host__ __device__ static int total(int N) { return 9 * N + 3 * N + 3 * N + 3 * N + 3 * N + 3 * N + 3 * N + 3 * N + 3 * N; }
+};
+__global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, int N, int ne, const double* __restrict__ S_rm,
+                                                             const double* __restrict__ ST_rm, const double* __restrict__ ptab,
+                                                             const double* __restrict__ ccw, double h0, double h1, double h2,
+                                                             const double* __restrict__ Q, const double* __restrict__ q0,
+                                                             const double* __restrict__ Gamma, const double* __restrict__ nin,
+                                                             const double* __restrict__ m, const double* __restrict__ M_tip,
+                                                             double* __restrict__ J) {
+    extern __shared__ __align__(16) double jsm[];
+    const int M = N - 1, n = 3 * ne;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* Ss = jsm;                 // [M][M] row-major
+    double* STs = jsm + M * M;        // [M][M] row-major
+    double* scr = jsm + 2 * M * M + warp * JacobianScratch::total(N);
+    double* Rn = scr;                 // [N][9] rotation matrices, row-major
+    double* bn = Rn + 9 * N;          // [N][3] R Gamma
+    double* nn = bn + 3 * N;          // [M][3] internal force at nodes 1..N-1
+    double* mn = nn + 3 * N;          // [N][3] internal couple, node 0 = M_tip
+    double* u = mn + 3 * N;           // [M][3]
+    double* th = u + 3 * N;           // [N][3] dtheta, base node = 0
+    double* v = th + 3 * N;           // [M][3]
+    double* dm = v + 3 * N;           // [N][3] dm, tip node = 0
+    double* wr = dm + 3 * N;          // [3][N] w_i drho_i
+    for (int e = threadIdx.x; e < M * M; e += blockDim.x) { Ss[e] = S_rm[e]; STs[e] = ST_rm[e]; }
+    __syncthreads();
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + warp; b < batch; b += warps_total) {
+        for (int i = lane; i < N; i += 32) {
+            sri::quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+            if (i < M) { const double* s = Q + b * 4 * M + i; q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M]; }
+            else if (q0) { const double* s = q0 + b * 4; q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3]; }
+            double* R = Rn + 9 * i;
+            sri::quat_to_rot_rm(q, R);
+            double g0 = 1.0, g1 = 0.0, g2 = 0.0;
+            if (Gamma) { const double* gm = Gamma + b * 3 * N + i; g0 = gm[0]; g1 = gm[N]; g2 = gm[2 * N]; }
+            bn[3 * i] = R[0] * g0 + R[1] * g1 + R[2] * g2;
+            bn[3 * i + 1] = R[3] * g0 + R[4] * g1 + R[5] * g2;
+            bn[3 * i + 2] = R[6] * g0 + R[7] * g1 + R[8] * g2;
+            if (i == 0) { const double* s = M_tip + b * 3; mn[0] = s[0]; mn[1] = s[1]; mn[2] = s[2]; }
+            else { const double* s = m + b * 3 * M + (i - 1); mn[3 * i] = s[0]; mn[3 * i + 1] = s[M]; mn[3 * i + 2] = s[2 * M]; }
+            if (i < M) { const double* s = nin + b * 3 * M + i; nn[3 * i] = s[0]; nn[3 * i + 1] = s[M]; nn[3 * i + 2] = s[2 * M]; }
+        }
+        if (lane < 3) { th[3 * M + lane] = 0.0; dm[lane] = 0.0; }
+        __syncwarp();
+        for (int d = 0; d < n; ++d) {
+            const int c = d / ne, k = d - c * ne;
+            const double hc = c == 0 ? h0 : (c == 1 ? h1 : h2);
+            for (int e = lane; e < 3 * M; e += 32) { const int i = e / 3, comp = e - 3 * i; u[e] = ptab[k * N + i] * Rn[9 * i + 3 * comp + c]; }
+            __syncwarp();
+            for (int e = lane; e < 3 * M; e += 32) {
+                const int i = e / 3, comp = e - 3 * i;
+                const double* srow = Ss + i * M;
+                double acc = 0.0;
+                for (int j = 0; j < M; ++j) acc = fma(srow[j], u[3 * j + comp], acc);
+                th[e] = acc;
+            }
+            __syncwarp();
+            for (int j = lane; j < M; j += 32) {  // node j + 1
+                const double* t = th + 3 * (j + 1); const double* bb = bn + 3 * (j + 1); const double* f = nn + 3 * j;
+                const double d0 = t[1] * bb[2] - t[2] * bb[1], d1 = t[2] * bb[0] - t[0] * bb[2], d2 = t[0] * bb[1] - t[1] * bb[0];
+                v[3 * j] = -(d1 * f[2] - d2 * f[1]);
+                v[3 * j + 1] = -(d2 * f[0] - d0 * f[2]);
+                v[3 * j + 2] = -(d0 * f[1] - d1 * f[0]);
+            }
+            __syncwarp();
+            for (int e = lane; e < 3 * M; e += 32) {
+                const int j = e / 3, comp = e - 3 * j;
+                const double* srow = STs + j * M;
+                double acc = 0.0;
+                for (int l = 0; l < M; ++l) acc = fma(srow[l], v[3 * l + comp], acc);
+                dm[3 + e] = acc;  // node j + 1
+            }
+            __syncwarp();
+            for (int i = lane; i < N; i += 32) {
+                const double* t = th + 3 * i; const double* mm = mn + 3 * i; const double* dmi = dm + 3 * i; const double* R = Rn + 9 * i;
+                const double t0 = dmi[0] - (t[1] * mm[2] - t[2] * mm[1]);
+                const double t1 = dmi[1] - (t[2] * mm[0] - t[0] * mm[2]);
+                const double t2 = dmi[2] - (t[0] * mm[1] - t[1] * mm[0]);
+                const double w = ccw[i], hk = hc * ptab[k * N + i];
+                wr[i] = w * ((c == 0 ? hk : 0.0) - (R[0] * t0 + R[3] * t1 + R[6] * t2));
+                wr[N + i] = w * ((c == 1 ? hk : 0.0) - (R[1] * t0 + R[4] * t1 + R[7] * t2));
+                wr[2 * N + i] = w * ((c == 2 ? hk : 0.0) - (R[2] * t0 + R[5] * t1 + R[8] * t2));
+            }
+            __syncwarp();
+            for (int jp = lane; jp < n; jp += 32) {
+                const int cp = jp / ne, kp = jp - cp * ne;
+                double acc = 0.0;
+                for (int i = 0; i < N; ++i) acc = fma(ptab[kp * N + i], wr[cp * N + i], acc);
+                J[(b * n + jp) * n + d] = acc;
+            }
+            __syncwarp();
+        }
     }
 }
 

@@ -8,7 +8,9 @@ with a forward-difference Jacobian: every column costs one fused four-stage inte
 iteration is 3*ne+1 integrations of the batch -- this driver is the hot path's main caller.  The 3*ne perturbed copies of
 the batch are integrated by ONE call of the hot path on 3*ne*B rods (jacobian="batched", the default: four library
 launches and four elementwise torch kernels per Jacobian, full waves on every SM); jacobian="columns" integrates them
-one after the other on the B-rod buffers (3*ne times the launches, 1/(3*ne) of the workspace).
+one after the other on the B-rod buffers (3*ne times the launches, 1/(3*ne) of the workspace).  jacobian="analytic" takes
+the Jacobian from sri_shape_jacobian instead (left-trivialised rotation variation: two contractions per direction, no
+integration): one integration of the batch per iteration.
 
 All arithmetic runs in this repository's CUDA kernels through the C ABI; torch supplies buffers, the trivial
 axpy-style updates of qe and the process group.  Multi-GPU: rods are sharded by index, the only collective is the
@@ -40,8 +42,8 @@ class StaticShapeSolver:
                  jacobian: str = "batched"):
         if not 1 <= ne <= 8:
             raise ValueError("1 <= ne <= 8")
-        if jacobian not in ("batched", "columns"):
-            raise ValueError('jacobian is "batched" or "columns"')
+        if jacobian not in ("batched", "columns", "analytic"):
+            raise ValueError('jacobian is "batched", "columns" or "analytic"')
         self.jacobian = jacobian
         self.h = integrator
         self.H = tuple(float(v) for v in H_diag)
@@ -53,8 +55,9 @@ class StaticShapeSolver:
     def residual(self, qe, F_tip, M_tip, K0=None, work=None, out=None, reduce=None):
         h = self.h
         K = h.strain_from_modes(qe, out=None if work is None else work["K"])
+        keep_n = work is not None and work.get("n") is not None   # the analytic Jacobian needs the internal force too
         res = h.integrate_all(K, F_tip, M_tip, Q=None if work is None else work["Q"], m=None if work is None else work["m"],
-                              want=("Q", "m"))
+                              n=work["n"] if keep_n else None, want=("Q", "n", "m") if keep_n else ("Q", "m"))
         if out is None and work is not None:
             out = work["g"]
         return h.galerkin_residual(K, self.H, res["Q"], res["m"], M_tip, self.ne, K0=K0, out=out, reduce=reduce)
@@ -71,7 +74,8 @@ class StaticShapeSolver:
             ws = {"K": e(B, 3, N), "Q": e(B, 4, M), "m": e(B, 3, M), "g": e(B, n),
                   "F": e(B, 3), "Mt": e(B, 3), "K0": e(B, 3, N) if has_K0 else None,
                   "qe": e(B, n), "g0": e(B, n), "J": e(B, n, n), "qp": e(B, n), "delta": e(B, n),
-                  "red": torch.zeros(2, dtype=f64, device=dev), "graph": None, "warmed": False, "wide": None}
+                  "red": torch.zeros(2, dtype=f64, device=dev), "graph": None, "warmed": False, "wide": None,
+                  "n": e(B, 3, M) if self.jacobian == "analytic" else None}
             if self.jacobian == "batched":  # the n perturbed copies of the batch, copy d = rods [d B, (d+1) B)
                 ws["wide"] = {"qe": e(n, B, n), "K": e(n * B, 3, N), "Q": e(n * B, 4, M), "m": e(n * B, 3, M),
                               "g": e(n * B, n), "F": e(n, B, 3), "Mt": e(n, B, 3),
@@ -91,7 +95,9 @@ class StaticShapeSolver:
         the whole batch), batched per-rod solve, update, residual of the new iterate."""
         qe, qp, g0, J = ws["qe"], ws["qp"], ws["g0"], ws["J"]
         n, B, wide = 3 * self.ne, ws["qe"].shape[0], ws["wide"]
-        if wide is not None:
+        if self.jacobian == "analytic":   # Q, n, m of the current iterate are in the workspace (last _evaluate)
+            self.h.shape_jacobian(ws["Q"], ws["n"], ws["m"], ws["Mt"], self.ne, self.H, out=J)
+        elif wide is not None:
             wq = wide["qe"]
             wq.copy_(qe.unsqueeze(0))
             wq.diagonal(dim1=0, dim2=2).add_(self.fd_step)            # copy d: qe + fd_step e_d
@@ -171,5 +177,5 @@ class StaticShapeSolver:
                 self._iteration(ws)
                 ws["warmed"] = True
             rep.iterations += 1
-            rep.integrations += n + 1
+            rep.integrations += 1 if self.jacobian == "analytic" else n + 1
         return ws["qe"].clone(), rep

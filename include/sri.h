@@ -174,10 +174,22 @@ int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, 
                           const double* Q, const double* q0, const double* m, const double* M_tip, double* g,
                           double* norm2_and_max);
 
+/* Jacobian of sri_galerkin_residual with respect to the modal strain coordinates, J[b][j][d] = d g_j / d qe_d, without
+ * any linear solve: the variation of the rotation is left-trivialised (dR = [dtheta]x R, dtheta' = R dK, dtheta(0) = 0), so
+ * every direction is two contractions with the cached integration matrices Dn_NN^-1 and D_TT^-1,
+ *   dtheta = Dn_NN^-1 (R dK),   dm = D_TT^-1 (-((dtheta x R Gamma) x n)),   drho = H dK - R^T (dm - dtheta x m).
+ * It is the tangent of the continuous problem collocated; it agrees with the exact tangent of the discrete stages to the
+ * discretisation error (1e-10 at N = 16, round-off at N = 32).  Q, n, m: the stage outputs at the current qe
+ * ([batch][4][M], [batch][3][M], [batch][3][M]); q0, Gamma optional as in sri_integrate_all; J [batch][3*ne][3*ne]
+ * row-major (the layout sri_solve_small_batched takes). */
+int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* Q, const double* q0,
+                       const double* Gamma, const double* n, const double* m, const double* M_tip, double* J);
+
 /* Newton iteration of the static shape problem (BASELINE configs[4]; rod_modeling.pdf section 2.2), the loop inside the
  * library: unknowns qe [batch][3*ne] (modal strain coordinates, in: initial guess, out: solution; device or host pointer),
  * residual g = sri_galerkin_residual of the four-stage integration of K = Phi qe under (F_tip, M_tip), forward-difference
- * Jacobian (the 3*ne perturbed copies of the batch go through ONE sri_integrate_all), per-rod solve, update; stops when
+ * Jacobian (the 3*ne perturbed copies of the batch go through ONE sri_integrate_all) or, with fd_step == 0, the
+ * analytic Jacobian of sri_shape_jacobian (one integration per iteration); per-rod solve, update; stops when
  * sqrt(sum g^2 / total_dof) < tol or after max_iter iterations (<= 62).  total_dof: number of unknowns over all ranks
  * (0 => batch*3*ne).  reduce (or NULL): called once per iteration with the 2 host doubles [sum g^2, max |g|] of this
  * rank's rods, must replace them by the sum / max over the ranks (e.g. MPI_Allreduce, ncclAllReduce + copy) and return 0
@@ -186,7 +198,7 @@ typedef int (*sri_allreduce_fn)(double* norm2_and_max, void* ctx);
 typedef struct sri_newton_report {
     int iterations;        /* Newton updates taken */
     int converged;         /* 1 when the tolerance was met */
-    int64_t integrations;  /* four-stage integrations of the batch: 1 + iterations * (3*ne + 1) */
+    int64_t integrations;  /* four-stage integrations of the batch: 1 + iterations * (3*ne + 1), or 1 + iterations (analytic) */
     double rms, max_abs;   /* of the last residual, over all ranks */
     double rms_history[64];
     int history_len;

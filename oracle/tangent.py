@@ -81,3 +81,48 @@ def galerkin_residual_and_jacobian(oracle, qe, F_tip, M_tip, H_diag, ne: int, K0
             drho = H[:, None] * dK - np.einsum("ikc,ik->ci", dRn, mn) - np.einsum("ikc,ik->ci", Rn, dmn)
             J[b, :, d] = np.einsum("ci,ki,i->ck", drho, P, w).reshape(n)
     return g, J
+
+
+def jacobian_by_quadrature(oracle, qe, F_tip, M_tip, H_diag, ne: int):
+    """The same Jacobian WITHOUT any linear solve: the variation of the rotation is left-trivialised, dR = [dtheta]x R with
+    dtheta' = R dK, dtheta(0) = 0, so every direction costs two contractions with the cached integration matrices
+        dtheta = Dn_NN^-1 (R dK),     dm = D_TT^-1 ( -((dtheta x b) x n) ),     b = R Gamma,
+        drho   = H dK - R^T (dm - dtheta x m).
+    It is the tangent of the continuous problem collocated, not of the discrete map: the two agree to the discretisation
+    error (1e-10 at N = 16, round-off at N = 32), far below what a Newton iteration can tell.  This is the formula of
+    sri_shape_jacobian; returns J [B][3 ne][3 ne]."""
+    N, M, n = oracle.N, oracle.M, 3 * ne
+    qe = np.ascontiguousarray(qe, dtype=np.float64).reshape(-1, n)
+    B = qe.shape[0]
+    H = np.asarray(H_diag, dtype=np.float64)
+    x = oracle.chebyshev_points()
+    P = np.stack([_L.legval(2 * x - 1, [0] * k + [1]) for k in range(ne)])
+    w = cc_weights(N)
+    Dn = oracle.dn()
+    S = np.linalg.inv(Dn[:M, :M]); S_T = np.linalg.inv(Dn[1:, 1:])
+    K = oracle.strain_from_modes(qe, ne)
+    out = oracle.integrate_all(K, F_tip, M_tip, explicit_inverse=False, want=("Q", "n", "m"))
+    return jacobian_by_quadrature_from_state(out["Q"], out["n"], out["m"], M_tip, H, ne, P, w, S, S_T)
+
+
+def jacobian_by_quadrature_from_state(Q, nn, mm, M_tip, H, ne, P, w, S, S_T):
+    B, _, M = Q.shape
+    N, n = M + 1, 3 * ne
+    e1 = np.array([1.0, 0.0, 0.0])
+    J = np.empty((B, n, n))
+    for b in range(B):
+        Rn = rotation(np.concatenate([Q[b].T, [[1.0, 0.0, 0.0, 0.0]]]))               # [N][3][3], base node = identity
+        mn = np.concatenate([[M_tip[b]], mm[b].T])                                     # node 0: M_tip
+        nj = nn[b].T                                                                   # nodes 1..N-1
+        bn = Rn @ e1
+        for d in range(n):
+            c, k = divmod(d, ne)
+            dK = np.zeros((3, N)); dK[c] = P[k]
+            u = np.einsum("ikc,ci->ik", Rn, dK)
+            th = np.concatenate([S @ u[:M], np.zeros((1, 3))])
+            v = -np.cross(np.cross(th, bn)[1:], nj)
+            dm = np.concatenate([np.zeros((1, 3)), S_T @ v])
+            tv = dm - np.cross(th, mn)
+            drho = H[:, None] * dK - np.einsum("ikc,ik->ci", Rn, tv)
+            J[b, :, d] = np.einsum("ci,ki,i->ck", drho, P, w).reshape(n)
+    return J

@@ -283,3 +283,57 @@ def test_cpp_host_drives_the_newton_solve(sri_lib):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.startswith("converged 1")
+
+
+@pytest.mark.parametrize("N,ne", [(16, 3), (16, 4), (9, 2), (32, 3)])
+def test_shape_jacobian_matches_the_restated_quadrature_formula(sri_lib, make_oracle, torch_mod, N, ne):
+    """sri_shape_jacobian (solve-free analytic Jacobian) against oracle/tangent.py's restatement on the same stage outputs;
+    that restatement is pinned on the CPU against the exact tangent of the discrete map and against central differences."""
+    from numpy.polynomial import legendre as L
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator
+    from oracle.tangent import cc_weights as ccw, jacobian_by_quadrature_from_state
+    o = make_oracle(N)
+    M = N - 1
+    B = 37
+    rng = np.random.default_rng(80 + N + ne)
+    qe = 0.7 * rng.normal(size=(B, 3 * ne))
+    F = rng.uniform(-1, 1, size=(B, 3)); Mt = rng.uniform(-0.5, 0.5, size=(B, 3))
+    H = np.array([1.0, 0.9, 0.77])
+    K = o.strain_from_modes(qe, ne)
+    ref = o.integrate_all(K, F, Mt, explicit_inverse=False, want=("Q", "n", "m"))
+    x = o.chebyshev_points()
+    P = np.stack([L.legval(2 * x - 1, [0] * k + [1]) for k in range(ne)])
+    Dn = o.dn()
+    J_ref = jacobian_by_quadrature_from_state(ref["Q"], ref["n"], ref["m"], Mt, H, ne, P, ccw(N), np.linalg.inv(Dn[:M, :M]),
+                                              np.linalg.inv(Dn[1:, 1:]))
+    t = lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()
+    with SpectralRodIntegrator(N, 0) as h:
+        J = h.shape_jacobian(t(ref["Q"]), t(ref["n"]), t(ref["m"]), t(Mt), ne, H)
+        J_host = h.shape_jacobian(ref["Q"][:5], ref["n"][:5], ref["m"][:5], Mt[:5], ne, H)
+        h.synchronize()
+    scale = np.abs(J_ref).max()
+    assert np.abs(J.cpu().numpy() - J_ref).max() <= 1e-12 * scale
+    assert np.abs(J_host - J_ref[:5]).max() <= 1e-12 * scale
+
+
+def test_newton_with_the_analytic_jacobian(h16, torch_mod):
+    """jacobian="analytic" (one integration per iteration) reaches the same shapes as the finite-difference Newton, in both
+    drivers, in at most one more iteration."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200.newton import StaticShapeSolver
+    B, ne = 600, 3
+    rng = np.random.default_rng(31)
+    F = np.zeros((B, 3)); F[:, 2] = -rng.uniform(0.1, 2.0, size=B); F[:, 1] = rng.uniform(-0.3, 0.3, size=B)
+    Mt = rng.uniform(-0.2, 0.2, size=(B, 3))
+    K0 = 0.2 * rng.normal(size=(B, 3, 1)) * np.ones((1, 1, 16))
+    tF, tM, tK0 = (torch_mod.from_numpy(np.ascontiguousarray(a)).cuda() for a in (F, Mt, K0))
+    H = (1.0, 1.0, 0.77)
+    for k0 in (None, tK0):
+        q_fd, rep_fd = StaticShapeSolver(h16, H, ne=ne).solve(tF, tM, K0=k0)
+        for use_graph in (False, True):
+            q_an, rep_an = StaticShapeSolver(h16, H, ne=ne, jacobian="analytic").solve(tF, tM, K0=k0, use_graph=use_graph)
+            assert rep_an.converged and rep_an.iterations <= rep_fd.iterations + 1
+            assert rep_an.integrations == rep_an.iterations + 1
+            assert np.abs(q_an.cpu().numpy() - q_fd.cpu().numpy()).max() <= 1e-9
+        q_c, rep_c = h16.newton_static_shape(tF, tM, ne, H, K0=k0, fd_step=0.0)
+        assert rep_c["converged"] and rep_c["iterations"] == rep_an.iterations and rep_c["integrations"] == rep_c["iterations"] + 1
+        assert np.abs(q_c.cpu().numpy() - q_fd.cpu().numpy()).max() <= 1e-9

@@ -425,3 +425,19 @@ def test_analytic_jacobian_of_the_discrete_static_shape_residual(oracle16):
             e = np.zeros(n); e[d] = h
             Jfd[:, :, d] = (g_of(qe + e) - g_of(qe - e)) / (2 * h)
         assert np.abs(J - Jfd).max() <= 1e-8 * np.abs(Jfd).max()
+
+
+@pytest.mark.parametrize("N,tol", [(16, 1e-9), (32, 1e-13)])
+def test_jacobian_by_quadrature_agrees_with_the_exact_tangent(make_oracle, N, tol):
+    """The solve-free Jacobian of sri_shape_jacobian (left-trivialised rotation variation: two contractions per direction)
+    against the exact tangent of the discrete map: equal to the discretisation error."""
+    from oracle.tangent import galerkin_residual_and_jacobian, jacobian_by_quadrature
+    o = make_oracle(N)
+    B, ne = 3, 3
+    rng = np.random.default_rng(1)
+    qe = 0.8 * rng.normal(size=(B, 3 * ne))
+    F = rng.uniform(-1, 1, size=(B, 3)); Mt = rng.uniform(-0.5, 0.5, size=(B, 3))
+    H = np.array([1.0, 0.9, 0.77])
+    _, J_exact = galerkin_residual_and_jacobian(o, qe, F, Mt, H, ne)
+    J = jacobian_by_quadrature(o, qe, F, Mt, H, ne)
+    assert np.abs(J - J_exact).max() <= tol * np.abs(J_exact).max()

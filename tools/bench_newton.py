@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rods", type=int, default=100000)
 ap.add_argument("--ne", type=int, default=3)
 ap.add_argument("--N", type=int, default=16)
-ap.add_argument("--jacobian", default="batched", choices=("batched", "columns"))
+ap.add_argument("--jacobian", default="batched", choices=("batched", "columns", "analytic"))
 ap.add_argument("--driver", default="python", choices=("python", "native"), help="newton.py (torch + CUDA graph) or sri_newton_static_shape (loop inside the C ABI)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -44,6 +44,7 @@ if args.driver == "native":
         norms[:] = t.cpu().numpy()
     def solve(use_graph=True):
         qe, rep = h.newton_static_shape(F, Mt, args.ne, (1.0, 1.0, 0.77), tol=1e-10, max_iter=30, total_dof=total_dof,
+                                        fd_step=0.0 if args.jacobian == "analytic" else 1e-6,
                                         allreduce=_allreduce if world > 1 else None)
         return qe, SimpleNamespace(**rep)
 else:
