@@ -1128,7 +1128,7 @@ int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag
         SRI_CUDA(cudaMemcpy(h->d_jac, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     constexpr int kWarps = 4;
-    const size_t smem = ((size_t)2 * M * M + (size_t)kWarps * JacobianScratch::total(N)) * sizeof(double);
+    const size_t smem = ((size_t)2 * M * M + (size_t)9 * N + (size_t)kWarps * JacobianScratch::total(N)) * sizeof(double);
     if (!h->jac_configured) {
         if (smem > 48 * 1024) SRI_CUDA(cudaFuncSetAttribute(shape_jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->jac_configured = true;

@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* Ss = jsm;                 // [M][M] row-major
     double* STs = jsm + M * M;        // [M][M] row-major
-    double* scr = jsm + 2 * M * M + warp * JacobianScratch::total(N);
+    double* Ps = jsm + 2 * M * M;     // [8][N] Legendre table
+    double* Ws = Ps + 8 * N;          // [N] quadrature weights
+    double* scr = Ws + N + warp * JacobianScratch::total(N);
     double* Rn = scr;                 // [N][9] rotation matrices, row-major
     double* bn = Rn + 9 * N;          // [N][3] R Gamma
     double* nn = bn + 3 * N;          // [M][3] internal force at nodes 1..N-1
@@ -309,6 +311,8 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
     double* dm = v + 3 * N;           // [N][3] dm, tip node = 0
     double* wr = dm + 3 * N;          // [3][N] w_i drho_i
     for (int e = threadIdx.x; e < M * M; e += blockDim.x) { Ss[e] = S_rm[e]; STs[e] = ST_rm[e]; }
+    for (int e = threadIdx.x; e < 8 * N; e += blockDim.x) Ps[e] = ptab[e];
+    for (int e = threadIdx.x; e < N; e += blockDim.x) Ws[e] = ccw[e];
     __syncthreads();
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + warp; b < batch; b += warps_total) {
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
         for (int d = 0; d < n; ++d) {
             const int c = d / ne, k = d - c * ne;
             const double hc = c == 0 ? h0 : (c == 1 ? h1 : h2);
-            for (int e = lane; e < 3 * M; e += 32) { const int i = e / 3, comp = e - 3 * i; u[e] = ptab[k * N + i] * Rn[9 * i + 3 * comp + c]; }
+            for (int e = lane; e < 3 * M; e += 32) { const int i = e / 3, comp = e - 3 * i; u[e] = Ps[k * N + i] * Rn[9 * i + 3 * comp + c]; }
             __syncwarp();
             for (int e = lane; e < 3 * M; e += 32) {
                 const int i = e / 3, comp = e - 3 * i;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
                 const double t0 = dmi[0] - (t[1] * mm[2] - t[2] * mm[1]);
                 const double t1 = dmi[1] - (t[2] * mm[0] - t[0] * mm[2]);
                 const double t2 = dmi[2] - (t[0] * mm[1] - t[1] * mm[0]);
-                const double w = ccw[i], hk = hc * ptab[k * N + i];
+                const double w = Ws[i], hk = hc * Ps[k * N + i];
                 wr[i] = w * ((c == 0 ? hk : 0.0) - (R[0] * t0 + R[3] * t1 + R[6] * t2));
                 wr[N + i] = w * ((c == 1 ? hk : 0.0) - (R[1] * t0 + R[4] * t1 + R[7] * t2));
                 wr[2 * N + i] = w * ((c == 2 ? hk : 0.0) - (R[2] * t0 + R[5] * t1 + R[8] * t2));
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
             for (int jp = lane; jp < n; jp += 32) {
                 const int cp = jp / ne, kp = jp - cp * ne;
                 double acc = 0.0;
-                for (int i = 0; i < N; ++i) acc = fma(ptab[kp * N + i], wr[cp * N + i], acc);
+                for (int i = 0; i < N; ++i) acc = fma(Ps[kp * N + i], wr[cp * N + i], acc);
                 J[(b * n + jp) * n + d] = acc;
             }
             __syncwarp();
