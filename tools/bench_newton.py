@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rods", type=int, default=100000)
 ap.add_argument("--ne", type=int, default=3)
 ap.add_argument("--N", type=int, default=16)
-ap.add_argument("--jacobian", default="batched", choices=("batched", "columns", "analytic"))
+ap.add_argument("--jacobian", default="analytic", choices=("analytic", "batched", "columns"), help="analytic: sri_shape_jacobian (one integration per iteration); batched / columns: forward differences")
 ap.add_argument("--driver", default="python", choices=("python", "native"), help="newton.py (torch + CUDA graph) or sri_newton_static_shape (loop inside the C ABI)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
