@@ -364,6 +364,33 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             hh.close()
             del Kh, Fh, Mh_t, fbh, outs
 
+    # ---- BASELINE configs[4] (Newton static shape solve of 10^5 tip-loaded rods), loop inside the C ABI; 1 GPU here, the
+    #      multi-GPU run with the residual all-reduce is tools/bench_newton.py.  Reported beside the headline, never fatal.
+    cfg5 = None
+    if world == 1:
+        try:
+            Bn, ne5, H5 = 100_000, 3, (1.0, 1.0, 0.77)
+            Fn = torch.empty((Bn, 3), dtype=f64, device=dev)
+            h.generate_rods(SEED, 0, Bn, None, Fn, None, None)
+            Fn[:, 2] = -(Fn[:, 2] + 1.0)
+            Fn[:, :2] = 0.0
+            Mn = torch.zeros((Bn, 3), dtype=f64, device=dev)
+            cfg5 = {"workload": "cfg5: Newton static shape solve of 10^5 tip-loaded rods (F_tip = (0,0,-f), f ~ U(0,2)), N=16, "
+                                "ne=3, H = diag(1,1,0.77), rms tolerance 1e-10, sri_newton_static_shape, 1 GPU"}
+            for name, fd_step in (("analytic_jacobian", 0.0), ("forward_difference_jacobian", 1e-6)):
+                h.newton_static_shape(Fn, Mn, ne5, H5, fd_step=fd_step)  # sizes the workspace of this mode
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                _, rep5 = h.newton_static_shape(Fn, Mn, ne5, H5, fd_step=fd_step)
+                torch.cuda.synchronize(dev)
+                dt5 = time.perf_counter() - t0
+                cfg5[name] = {"seconds": dt5, "converged": rep5["converged"], "newton_iterations": rep5["iterations"],
+                              "integrations_of_the_batch": rep5["integrations"], "rod_solves_per_s": Bn / dt5,
+                              "final_rms": rep5["rms"]}
+            del Fn, Mn
+        except Exception as exc:  # noqa: BLE001 -- a side leg must not take the headline measurement down
+            cfg5 = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank != 0:
         return
 
@@ -416,6 +443,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         line["other_configs"] = {"cfg2": cfg2}
         if cfg4:
             line["other_configs"]["cfg4"] = cfg4
+        if cfg5:
+            line["other_configs"]["cfg5"] = cfg5
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     print(json.dumps(line), flush=True)
