@@ -1,9 +1,9 @@
 """Exact tangent of the DISCRETE four-stage map and of the Galerkin residual of the static shape problem, in numpy.
 
-TEST INFRASTRUCTURE ONLY (like everything under oracle/): nothing in the product imports this.  It pins the formulas of
-the analytic Newton Jacobian that DESIGN.md section 7 names as the next step for SURVEY 8 f1 -- the 3*ne tangent systems
-share the stage-1 operator A_NN(K) (main.cpp:55-88), so on the GPU they are extra right-hand-side columns of one
-elimination instead of 3*ne integrations.
+TEST INFRASTRUCTURE ONLY (like everything under oracle/): nothing in the product imports this.  Two restatements of the
+Newton Jacobian of SURVEY 8 f1: (1) the exact tangent of the discrete stages -- the 3*ne tangent systems share the stage-1
+operator A_NN(K) (main.cpp:55-88) -- pinned against central differences of the oracle's own residual; (2) the solve-free
+form that sri_shape_jacobian computes on the GPU (jacobian_by_quadrature, at the end of this file), pinned against (1).
 
 With Qs the stage-1 solution (stack [c*M+i], main.cpp:80-81) and a strain direction dK [3][N]:
     A_NN(K) dQs = 1/2 calA(dK) Qs                      (calA: the block-diagonal of updateA, main.cpp:72-75, linear in K)
