@@ -81,6 +81,7 @@ class Oracle:
         L.sri_oracle_wrench_local_solve.argtypes = [c_void_p] * 10
         L.sri_oracle_max_threads.restype = c_int
         L.sri_oracle_generate_rods.argtypes = [c_int, ctypes.c_uint64, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.sri_oracle_generate_modes.argtypes = [ctypes.c_uint64, c_long, c_long, c_void_p]
         self._ops = L.sri_oracle_ops_create(self.N)
 
     def __del__(self):  # pragma: no cover
@@ -197,6 +198,12 @@ class Oracle:
         K = np.empty((batch, 3, self.N)); F = np.empty((batch, 3)); Mt = np.empty((batch, 3)); fb = np.empty((batch, 3, self.N))
         self.lib.sri_oracle_generate_rods(self.N, seed, first_rod, batch, K.ctypes.data, F.ctypes.data, Mt.ctypes.data, fb.ctypes.data)
         return K, F, Mt, fb
+
+    def generate_modes(self, seed: int, first_rod: int, batch: int) -> np.ndarray:
+        """qe [batch][9] of the rods generate_rods() samples: K_c = qe[3c] P_0 + qe[3c+1] P_1(2X-1)."""
+        qe = np.empty((batch, 9))
+        self.lib.sri_oracle_generate_modes(seed, first_rod, batch, qe.ctypes.data)
+        return qe
 
     def max_threads(self) -> int:
         return int(self.lib.sri_oracle_max_threads())

@@ -627,6 +627,23 @@ void sri_oracle_generate_rods(int N, uint64_t seed, long first_rod, long batch, 
     free(x);
 }
 
+/* The modal coordinates behind sri_oracle_generate_rods' curvature: qe[b][3c+0] = alpha, [3c+1] = beta, [3c+2] = 0, i.e.
+ * K_c = alpha P_0 + beta P_1(2X-1) in the reference's Phi<3,3> basis (include/utilities.h:49-67, main.cpp:17,69), so the
+ * same rods can be handed to the reference's own integrateQuaternions()/integratePosition() (oracle/reference_harness.cpp). */
+void sri_oracle_generate_modes(uint64_t seed, long first_rod, long batch, double* qe)
+{
+    for (long b = 0; b < batch; ++b) {
+        const uint64_t rod = (uint64_t)(first_rod + b);
+        uint32_t w[4];
+        for (int c = 0; c < 3; ++c) {
+            philox4x32_10((uint32_t)rod, (uint32_t)(rod >> 32), (uint32_t)c, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+            qe[b * 9 + 3 * c + 0] = 4.0 * u01(w[0], w[1]) - 2.0;
+            qe[b * 9 + 3 * c + 1] = 4.0 * u01(w[2], w[3]) - 2.0;
+            qe[b * 9 + 3 * c + 2] = 0.0;
+        }
+    }
+}
+
 /* raw Philox block for the known-answer test in tests/ */
 void sri_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {

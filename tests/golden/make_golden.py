@@ -7,6 +7,10 @@ reference_main_default.json  -- output of the reference's own main() (compiled v
 oracle_default_stages34.json -- stages 3-4 for the same rod (F_tip=(0,0,-1), M_tip=0); the reference does not
                                 implement them, so this file is produced by the oracle and pinned by the analytic
                                 known-answer tests in tests/test_oracle_cpu.py.
+reference_random_rods.npz    -- 1024 rods of the benchmark's Philox stream (seed 0x5EED, rods 0..1023) through the reference's
+                                OWN integrateQuaternions() / integratePosition() (oracle/reference_harness.cpp #includes
+                                /root/reference/main.cpp): qe [1024][9], the reference's strain samples K [1024][3][16],
+                                Q [1024][4][15], r [1024][3][15], and A_NN of updateA (main.cpp:55-88) for rods 0..3; exact FP64.
 """
 import json
 import sys
@@ -44,4 +48,13 @@ out = o.integrate_all(K, F, Mt)
     "n": [[repr(float(v)) for v in row] for row in out["n"][0]],
     "m": [[repr(float(v)) for v in row] for row in out["m"][0]],
 }, indent=1))
+from oracle.build_reference import ReferenceHarness  # noqa: E402
+
+NR = 1024
+qe = o.generate_modes(0x5EED, 0, NR)
+harness = ReferenceHarness()
+ref = harness.integrate(qe)
+A = np.stack([harness.update_A(qe[b]) for b in range(4)])
+np.savez_compressed(HERE / "reference_random_rods.npz", qe=qe, K=ref["K"], Q=ref["Q"], r=ref["r"], A_NN=A,
+                    seed=np.uint64(0x5EED), first_rod=np.int64(0))
 print("golden fixtures written to", HERE)
