@@ -5,6 +5,7 @@ Python host-side mirror used by tests, bench.py and the Newton shape driver.  Im
 """
 from .api import (  # noqa: F401
     ComputeChebyshevPoints,
+    MultiDeviceIntegrator,
     GetCoefficients_c,
     Phi,
     SpectralRodIntegrator,
@@ -13,11 +14,13 @@ from .api import (  # noqa: F401
     integratePosition,
     integrateQuaternions,
     kernel_launch_count,
+    scale_for_length,
+    shard_range,
     skew,
 )
 from ._lib import SriError  # noqa: F401
 
 __all__ = [
     "ComputeChebyshevPoints", "GetCoefficients_c", "Phi", "SpectralRodIntegrator", "getDn",
-    "integratePosition", "integrateQuaternions", "kernel_launch_count", "SriError", "skew", "ad",
+    "integratePosition", "integrateQuaternions", "kernel_launch_count", "SriError", "skew", "ad", "MultiDeviceIntegrator", "shard_range", "scale_for_length",
 ]

@@ -45,6 +45,7 @@ class NewtonReport(ctypes.Structure):
     _fields_ = [
         ("iterations", c_int), ("converged", c_int), ("integrations", c_int64),
         ("rms", c_double), ("max_abs", c_double), ("rms_history", c_double * 64), ("history_len", c_int),
+        ("singular_solves", c_int64),
     ]
 
 
@@ -64,6 +65,21 @@ SYMBOLS = {
     "sri_get_N": (c_int, [c_void_p, POINTER(c_int)]),
     "sri_get_operator": (c_int, [c_void_p, c_int, c_void_p]),
     "sri_strain_from_modes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "sri_assemble_A": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "sri_device_count": (c_int, [POINTER(c_int)]),
+    "sri_create_multi": (c_int, [c_int, POINTER(c_int), c_int, POINTER(c_void_p)]),
+    "sri_destroy_multi": (c_int, [c_void_p]),
+    "sri_multi_device_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "sri_multi_get_handle": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    "sri_shard_range": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
+    "sri_integrate_all_sharded": (c_int, [c_void_p, POINTER(RodBatch)]),
+    "sri_integrate_all_per_device": (c_int, [c_void_p, POINTER(RodBatch)]),
+    "sri_newton_static_shape_sharded": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                                c_int, c_double, POINTER(NewtonReport)]),
+    "sri_nccl_unique_id": (c_int, [c_void_p]),
+    "sri_nccl_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "sri_nccl_finalize": (c_int, [c_void_p]),
+    "sri_nccl_allreduce_norms": (c_int, [c_void_p, c_void_p]),
     "sri_integrate_quaternions": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_integrate_position": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_integrate_stress": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -183,6 +183,42 @@ class SpectralRodIntegrator:
         _lib.check(self._lib.sri_strain_from_modes(self._h, batch, ne, _ptr(qe, "qe"), _ptr(K, "K")), "sri_strain_from_modes")
         return K
 
+    def assemble_A(self, K, out=None):
+        """A_NN [batch][4M][4M] of updateA (main.cpp:55-88), returned row/column indexed as A[b, row, col]."""
+        self._follow_torch(K)
+        batch, n = K.shape[0], 4 * self.M
+        buf = out if out is not None else _empty_like_kind(K, (batch, n, n))
+        _lib.check(self._lib.sri_assemble_A(self._h, batch, _ptr(K, "K"), _ptr(buf, "A_NN")), "sri_assemble_A")
+        return buf.transpose(1, 2) if _is_torch(buf) else buf.transpose(0, 2, 1)  # the ABI is column-major like Eigen
+
+    # -- NCCL residual-norm reduction of the Newton driver (one process per GPU)
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _lib.check(_lib.load().sri_nccl_unique_id(buf), "sri_nccl_unique_id")
+        return buf.raw
+
+    def nccl_init(self, nranks: int, rank: int, unique_id: bytes) -> None:
+        """Collective over the ranks: attaches an NCCL communicator to this handle (sri_nccl_init)."""
+        assert len(unique_id) == 128
+        _lib.check(self._lib.sri_nccl_init(self._h, int(nranks), int(rank), ctypes.c_char_p(unique_id)), "sri_nccl_init")
+
+    def nccl_init_from_torch(self, group=None) -> None:
+        """nccl_init with the unique id broadcast from rank 0 over an initialised torch.distributed process group."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.nccl_init(world, rank, box[0])
+
+    def nccl_finalize(self) -> None:
+        _lib.check(self._lib.sri_nccl_finalize(self._h), "sri_nccl_finalize")
+
+    def nccl_allreduce_norms(self, norm2_and_max) -> None:
+        """In place on a 2-element CUDA tensor: (sum over ranks, max over ranks), asynchronous on the handle's stream."""
+        self._follow_torch(norm2_and_max)
+        _lib.check(self._lib.sri_nccl_allreduce_norms(self._h, _ptr(norm2_and_max, "norms")), "sri_nccl_allreduce_norms")
+
     def integrate_quaternions(self, K, q0=None, out=None, info=None):
         self._follow_torch(K)
         batch = K.shape[0]
@@ -365,8 +401,7 @@ class SpectralRodIntegrator:
         if failure:
             raise failure[0]
         _lib.check(rc, "sri_newton_static_shape")
-        return qe, {"iterations": rep.iterations, "converged": bool(rep.converged), "integrations": rep.integrations,
-                    "rms": rep.rms, "max_abs": rep.max_abs, "rms_history": list(rep.rms_history[:rep.history_len])}
+        return qe, _report_dict(rep)
 
     def solve_small_batched(self, A, b, out=None, info=None):
         """A [batch][n][n] (row-major, destroyed), b [batch][n] -> x [batch][n]; CUDA tensors only."""
@@ -401,6 +436,103 @@ class SpectralRodIntegrator:
         v = ctypes.c_double()
         _lib.check(self._lib.sri_measure_dmma_peak(self._h, ctypes.byref(v)), "sri_measure_dmma_peak")
         return v.value
+
+
+def scale_for_length(length, K, Gamma=None, fbar=None, lbar=None):
+    """Inputs of a rod of length `length` (scalar, or one value per rod) for the unit-interval integrators.
+
+    The reference integrates on X in [0, 1] with an implicit rod length of 1 (main.cpp:15 uses ComputeChebyshevPoints<N, 1>).
+    For a rod of length l every ODE is multiplied by l (rod_modeling.pdf eq. 2.17): Q' = l/2 Q (x) (0,K), r' = l R Gamma,
+    n' = -l fbar, m' = -(r' x n + l lbar), so the library is called with (l K, l Gamma, l fbar, l lbar); the tip loads and
+    every output (Q, r, n, m at the nodes X_i = s_i / l) are unchanged.  Gamma = None means (1,0,0) and becomes (l,0,0).
+    Returns (K, Gamma, fbar, lbar) scaled, same array kind as K; None stays None for the loads."""
+    if _is_torch(K):
+        ell = torch.as_tensor(length, dtype=K.dtype, device=K.device).reshape(-1, 1, 1)
+    else:
+        ell = np.asarray(length, dtype=np.float64).reshape(-1, 1, 1)
+    if Gamma is None:
+        e1 = (torch.zeros_like(K) if _is_torch(K) else np.zeros_like(K))
+        e1[:, 0, :] = 1.0
+        Gamma = e1
+    sc = lambda a: None if a is None else (a * ell).contiguous() if _is_torch(a) else np.ascontiguousarray(a * ell)
+    return sc(K), sc(Gamma), sc(fbar), sc(lbar)
+
+
+def _report_dict(rep) -> dict:
+    return {"iterations": rep.iterations, "converged": bool(rep.converged), "integrations": rep.integrations,
+            "rms": rep.rms, "max_abs": rep.max_abs, "rms_history": list(rep.rms_history[:rep.history_len]),
+            "singular_solves": rep.singular_solves}
+
+
+def shard_range(total: int, rank: int, world: int):
+    """sri_shard_range: [floor(rank*total/world), floor((rank+1)*total/world))."""
+    a, b = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(_lib.load().sri_shard_range(int(total), int(rank), int(world), ctypes.byref(a), ctypes.byref(b)), "sri_shard_range")
+    return int(a.value), int(b.value)
+
+
+class MultiDeviceIntegrator:
+    """sri_multi_handle: one operator set per device, rods sharded by index, one host thread per device inside the library
+    (the C/C++ host's multi-GPU path; bench.py uses one process per GPU instead)."""
+
+    def __init__(self, N: int = 16, devices=None, ndev: int = None):
+        self._lib = _lib.load()
+        self._mh = ctypes.c_void_p()
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            _lib.check(self._lib.sri_create_multi(int(N), arr, len(devices), ctypes.byref(self._mh)), "sri_create_multi")
+        else:
+            _lib.check(self._lib.sri_create_multi(int(N), None, int(ndev), ctypes.byref(self._mh)), "sri_create_multi")
+        self.N, self.M = int(N), int(N) - 1
+
+    def close(self) -> None:
+        if getattr(self, "_mh", None) is not None and self._mh:
+            self._lib.sri_destroy_multi(self._mh)
+            self._mh = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self) -> int:
+        v = ctypes.c_int()
+        _lib.check(self._lib.sri_multi_device_count(self._mh, ctypes.byref(v)), "sri_multi_device_count")
+        return v.value
+
+    def integrate_all(self, K, F_tip=None, M_tip=None, q0=None, r0=None, Gamma=None, fbar=None, lbar=None, info=None,
+                      want=("Q", "r", "n", "m")):
+        """Host (numpy / CPU torch) buffers, sharded over the devices; returns the requested outputs as numpy arrays."""
+        batch = K.shape[0]
+        shapes = {"Q": (batch, 4, self.M), "r": (batch, 3, self.M), "n": (batch, 3, self.M), "m": (batch, 3, self.M)}
+        outs = {k: (np.empty(shapes[k]) if k in want else None) for k in "Qrnm"}
+        rb = _lib.RodBatch(
+            batch=batch, K=_ptr(K, "K"), q0=_ptr(q0, "q0"), r0=_ptr(r0, "r0"), Gamma=_ptr(Gamma, "Gamma"),
+            fbar=_ptr(fbar, "fbar"), lbar=_ptr(lbar, "lbar"), F_tip=_ptr(F_tip, "F_tip"), M_tip=_ptr(M_tip, "M_tip"),
+            Q=_ptr(outs["Q"], "Q"), r=_ptr(outs["r"], "r"), n=_ptr(outs["n"], "n"), m=_ptr(outs["m"], "m"),
+            info=_ptr(info, "info", np.int32))
+        _lib.check(self._lib.sri_integrate_all_sharded(self._mh, ctypes.byref(rb)), "sri_integrate_all_sharded")
+        return {k: v for k, v in outs.items() if v is not None}
+
+    def newton_static_shape(self, F_tip, M_tip, ne: int, H_diag=(1.0, 1.0, 0.77), qe=None, K0=None, tol: float = 1e-10,
+                            max_iter: int = 30, fd_step: float = 0.0):
+        batch = F_tip.shape[0]
+        if qe is None:
+            qe = np.zeros((batch, 3 * int(ne)))
+        H = np.ascontiguousarray(np.asarray(H_diag, dtype=np.float64))
+        rep = _lib.NewtonReport()
+        _lib.check(self._lib.sri_newton_static_shape_sharded(
+            self._mh, batch, int(ne), H.ctypes.data, _ptr(F_tip, "F_tip"), _ptr(M_tip, "M_tip"), _ptr(K0, "K0"), _ptr(qe, "qe"),
+            float(tol), int(max_iter), float(fd_step), ctypes.byref(rep)), "sri_newton_static_shape_sharded")
+        return qe, _report_dict(rep)
 
 
 def kernel_launch_count() -> int:

@@ -2,15 +2,21 @@
 #include "../../include/sri.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "sri_fused16.cuh"
@@ -73,25 +79,34 @@ struct sri_context {
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
     double* d_ptab = nullptr;    // Legendre polynomials at the nodes, P_k(2 x_i - 1), [8][N]
     double* d_jac = nullptr;     // S = Dn_NN^-1 and S_T = D_TT^-1, row-major [M][M] each (sri_shape_jacobian), built on first use
-    bool jac_configured = false;
+    double* d_dnn = nullptr;     // Dn_NN, column-major [M][M] (sri_assemble_A), built on first use
+    const int* skip = nullptr;   // Newton loop with the device-side convergence flag: kernels launched while this is set take
+                                 // it as their "already converged, do nothing" flag (NULL everywhere else)
+    void* nccl_comm = nullptr;   // ncclComm_t attached by sri_nccl_init
+    int nccl_nranks = 1, nccl_rank = 0;
+    double* d_gather = nullptr;  // [2 * nccl_nranks] all-gathered norms
     int fused_blocks_per_sm = 0;
     int stage_blocks_per_sm = 0;
     int dmma_blocks_per_sm = 0;
     double dmma_growth = sri::kDmmaGrowthDefault;
     bool use_dmma = false;
-    bool wrench_configured = false, solve_small_configured = false;
     struct NewtonWorkspace {  // buffers of sri_newton_static_shape, kept for the next call of the same shape
         int64_t B = -1; int ne = 0; bool has_K0 = false, analytic = false;
         double* block = nullptr;
         double *K, *Q, *m, *nn, *g0, *J, *delta, *qe, *red, *F, *Mt, *K0, *qw, *Kw, *Qw, *mw, *gw, *Fw, *Mtw, *K0w;
+        int* sinfo = nullptr;            // [B] zero-pivot report of the per-rod Newton solve
+        sri::NewtonState* state = nullptr;       // device: convergence flag, singular count, norm history
+        sri::NewtonState* host_state = nullptr;  // pinned mirror, filled by an asynchronous copy after every test
+        cudaEvent_t ev[2] = {nullptr, nullptr};
     } newton;
     double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
     size_t partial_cap = 0;
     unsigned* d_counter = nullptr;
-    size_t tma_smem[3] = {0, 0, 0};  // last shared-memory size configured per TMA stage kernel, and its occupancy
+    size_t tma_smem[3] = {0, 0, 0};  // shared-memory size the cached occupancy of each TMA stage kernel was computed for
     int tma_occ[3] = {0, 0, 0};
     size_t gtma_smem[3] = {0, 0, 0};  // the same for the 17 <= N <= 64 TMA stage kernels
     int gtma_occ[3] = {0, 0, 0};
+    cudaEvent_t pipe_event = nullptr;  // orders the host-buffer pipeline after the work already queued on `stream`
     int stage_impl = 0;          // N <= 16 separate-stage entry points: 0 = measured best per stage (position, couple: TMA-staged;
                                  // stress: direct loads), 1 = SRI_STAGE_IMPL=tma everywhere, 2 = SRI_STAGE_IMPL=ldg everywhere       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
     // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
@@ -174,6 +189,49 @@ private:
         if (rc__ != SRI_OK) return rc__; \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, device), not of a handle: keep one process-wide
+// high-water mark per (kernel, device) that only grows, so that handles with different N / optional inputs on the same GPU
+// cannot lower the limit under each other.
+template <typename Kernel>
+int ensure_dynamic_smem(Kernel kernel, int device, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> high;
+    if (bytes <= 48 * 1024) return SRI_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = high[{reinterpret_cast<const void*>(kernel), device}];
+    if (bytes > cur) {
+        SRI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return SRI_OK;
+}
+
+// Makes the handle's device current for the duration of one API call and restores the caller's device afterwards.
+class DeviceGuard {
+public:
+    DeviceGuard() = default;
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+    int enter(sri_context* h) {
+        if (!h) return fail(SRI_ERR_INVALID_ARGUMENT, "null handle");
+        if (cudaGetDevice(&prev_) != cudaSuccess) { cudaGetLastError(); prev_ = -1; }
+        if (prev_ != h->device) {
+            cudaError_t e = cudaSetDevice(h->device);
+            if (e != cudaSuccess) return fail(SRI_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+            restore_ = prev_ >= 0;
+        }
+        return SRI_OK;
+    }
+    ~DeviceGuard() { if (restore_) cudaSetDevice(prev_); }
+
+private:
+    int prev_ = -1;
+    bool restore_ = false;
+};
+#define SRI_ENTER(h)          \
+    DeviceGuard guard__;      \
+    SRI_TRY(guard__.enter(h))
+
 }  // namespace
 
 #include "sri_small_kernels.cuh"  // strain / residual / projection / Newton helper / peak kernels
@@ -248,7 +306,7 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
                    int list_slot = 3) {
     if (p_in.batch <= 0) return SRI_OK;
     sri::FusedParams p = p_in;
-    if (use_handle_stream) stream = h->stream;
+    if (use_handle_stream) { stream = h->stream; p.skip = h->skip; }
     if (h->R != 0) return launch_generic<SOLVE>(h, p, stream, list_slot);
     const long long pairs = (p.batch + 1) / 2;
     const long long want = (pairs + (kFusedThreads / 32) - 1) / (kFusedThreads / 32);
@@ -293,6 +351,18 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
 
 // ---- host-buffer pipeline --------------------------------------------------------------------------------------
 
+// Host-buffer calls with an info array: every output has landed; report SRI_ERR_SINGULAR when any rod met a zero or
+// non-finite pivot (info[b] != 0).  The other rods' results are valid.
+int singular_status(const int* info_host, int64_t batch, const char* where) {
+    if (!info_host) return SRI_OK;
+    int64_t bad = 0, first = -1;
+    for (int64_t b = 0; b < batch; ++b)
+        if (info_host[b] != 0) { if (!bad) first = b; ++bad; }
+    if (!bad) return SRI_OK;
+    return fail(SRI_ERR_SINGULAR, std::string(where) + ": " + std::to_string(bad) + " rod(s) met a zero or non-finite pivot (first: rod " +
+                                      std::to_string(first) + ", info = " + std::to_string(info_host[first]) + "); see the info array");
+}
+
 bool all_host_pointers(const sri_rod_batch* r) {
     const void* ptrs[] = {r->K, r->q0, r->r0, r->Gamma, r->fbar, r->lbar, r->F_tip, r->M_tip, r->Q, r->r, r->n, r->m, r->info};
     for (const void* p : ptrs)
@@ -314,8 +384,26 @@ int pipe_reserve(sri_context* h, int slot, int arr, size_t bytes, void** out) {
 
 // All buffers live on the host: split the batch into chunks and overlap the H2D copy of chunk c+1, the kernel of
 // chunk c and the D2H copy of chunk c-1 on three streams (pinned host memory makes the copies truly asynchronous;
-// pageable memory still works, serialised by the driver).  Returns after every result has landed.
+// pageable memory still works, serialised by the driver).  Returns after every result has landed.  The pipeline is ordered
+// after whatever the caller has already queued on the handle's stream (e.g. an asynchronous copy that fills a pinned input
+// buffer), and when a step fails it drains the copies already in flight before the error is returned.
+int integrate_all_host_pipeline_body(sri_context* h, const sri_rod_batch* r);
 int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
+    for (int sl = 0; sl < sri_context::kPipeSlots; ++sl)
+        if (!h->pipe_stream[sl]) SRI_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[sl], cudaStreamNonBlocking));
+    if (!h->pipe_event) SRI_CUDA(cudaEventCreateWithFlags(&h->pipe_event, cudaEventDisableTiming));
+    SRI_CUDA(cudaEventRecord(h->pipe_event, h->stream));
+    for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) SRI_CUDA(cudaStreamWaitEvent(h->pipe_stream[sl], h->pipe_event, 0));
+    const int rc = integrate_all_host_pipeline_body(h, r);
+    if (rc != SRI_OK) {
+        const std::string keep = g_last_error;
+        for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) cudaStreamSynchronize(h->pipe_stream[sl]);
+        cudaGetLastError();
+        g_last_error = keep;
+    }
+    return rc;
+}
+int integrate_all_host_pipeline_body(sri_context* h, const sri_rod_batch* r) {
     const int N = h->N, M = h->M;
     const int64_t B = r->batch;
     // chunk schedule: a short first chunk fills the pipeline quickly (its H2D copy and kernel are the only work that is
@@ -323,8 +411,6 @@ int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
     // set-up of the copy engines does not show
     const int64_t chunk = (N <= 16) ? 65536 : (N <= 32 ? 16384 : 4096);
     const int64_t first_chunk = chunk / 8;
-    for (int sl = 0; sl < sri_context::kPipeSlots; ++sl)
-        if (!h->pipe_stream[sl]) SRI_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[sl], cudaStreamNonBlocking));
     struct Arr { const void* src; void* dst; size_t per_rod; };
     int c = 0;
     for (int64_t first = 0, step = first_chunk; first < B; first += step, step = chunk, ++c) {
@@ -364,7 +450,7 @@ int integrate_all_host_pipeline(sri_context* h, const sri_rod_batch* r) {
         }
     }
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) SRI_CUDA(cudaStreamSynchronize(h->pipe_stream[sl]));
-    return SRI_OK;
+    return singular_status(r->info, B, "sri_integrate_all");
 }
 
 template <int STAGE>
@@ -437,8 +523,8 @@ int launch_stage(sri_context* h, const sri::FusedParams& p_in) {
     L.out = 2 * off;
     L.warp_bytes = 2 * off + 8 * 3 * M * 8;
     const size_t smem = (size_t)sri::kStageTmaWarps * L.warp_bytes;
+    SRI_TRY(ensure_dynamic_smem(sri::stage_tma_kernel<STAGE>, h->device, smem));
     if (h->tma_smem[STAGE] != smem) {  // the layout depends on which optional inputs are present
-        SRI_CUDA(cudaFuncSetAttribute(sri::stage_tma_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tma_occ[STAGE], sri::stage_tma_kernel<STAGE>, 32 * sri::kStageTmaWarps, smem));
         h->tma_smem[STAGE] = smem;
     }
@@ -506,12 +592,12 @@ int launch_stage_generic(sri_context* h, const sri::FusedParams& p_in) {
     if (off == 0) return launch_stage_generic_direct<STAGE>(h, p);  // nothing to stage (force stage without inputs)
     const size_t smem = (size_t)h->R * h->R * sizeof(double) + (size_t)4 * off;
     if (smem > 220 * 1024) return launch_stage_generic_direct<STAGE>(h, p);
+    if (h->R == 32) SRI_TRY(ensure_dynamic_smem(sri::stage_generic_tma_kernel<STAGE, 32>, h->device, smem));
+    else SRI_TRY(ensure_dynamic_smem(sri::stage_generic_tma_kernel<STAGE, 64>, h->device, smem));
     if (h->gtma_smem[STAGE] != smem) {
         if (h->R == 32) {
-            SRI_CUDA(cudaFuncSetAttribute(sri::stage_generic_tma_kernel<STAGE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->gtma_occ[STAGE], sri::stage_generic_tma_kernel<STAGE, 32>, 128, smem));
         } else {
-            SRI_CUDA(cudaFuncSetAttribute(sri::stage_generic_tma_kernel<STAGE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->gtma_occ[STAGE], sri::stage_generic_tma_kernel<STAGE, 64>, 128, smem));
         }
         h->gtma_smem[STAGE] = smem;
@@ -526,13 +612,6 @@ int launch_stage_generic(sri_context* h, const sri::FusedParams& p_in) {
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     if (tiles * 8 < p.batch) return launch_stage_generic_direct<STAGE>(h, stage_tail(p, tiles * 8));
-    return SRI_OK;
-}
-
-int check_handle(sri_handle h) {
-    if (!h) return fail(SRI_ERR_INVALID_ARGUMENT, "null handle");
-    cudaError_t e = cudaSetDevice(h->device);
-    if (e != cudaSuccess) return fail(SRI_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
     return SRI_OK;
 }
 
@@ -584,11 +663,13 @@ int sri_create(int N, int device, sri_handle* out) {
     int ndev = 0;
     SRI_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(SRI_ERR_CUDA, "sri_create: no such CUDA device (there is no CPU fallback)");
-    SRI_CUDA(cudaSetDevice(device));
     sri_context* h = new (std::nothrow) sri_context();
     if (!h) return fail(SRI_ERR_ALLOC, "sri_create: out of host memory");
     h->N = N; h->M = N - 1; h->device = device;
-    if (!h->ops.build(N)) { delete h; return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create: singular differentiation block"); }
+    DeviceGuard guard;  // restores the caller's current device on every path out of this function
+    const int rc = [&]() -> int {
+    SRI_TRY(guard.enter(h));
+    if (!h->ops.build(N)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create: singular differentiation block");
     cudaDeviceProp prop;
     SRI_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
@@ -675,25 +756,25 @@ int sri_create(int N, int device, sri_handle* out) {
             SRI_CUDA(cudaMemcpy(h->d_ops2, t2.data(), sizeof(double) * t2.size(), cudaMemcpyHostToDevice));
             if (R == 32) {
                 using Cfg = sri::TiledDmmaCfg<SRI_T32>;
-                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<SRI_T32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+                SRI_TRY(ensure_dynamic_smem(sri::tiled_dmma_kernel<SRI_T32>, h->device, Cfg::smem_bytes));
                 SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<SRI_T32>, Cfg::threads, Cfg::smem_bytes));
             } else {
                 using Cfg = sri::TiledDmmaCfg<SRI_T64>;
-                SRI_CUDA(cudaFuncSetAttribute(sri::tiled_dmma_kernel<SRI_T64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+                SRI_TRY(ensure_dynamic_smem(sri::tiled_dmma_kernel<SRI_T64>, h->device, Cfg::smem_bytes));
                 SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::tiled_dmma_kernel<SRI_T64>, Cfg::threads, Cfg::smem_bytes));
             }
-            if (h->dmma_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
+            if (h->dmma_blocks_per_sm < 1) { return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
         }
         if (h->R == 32) {
             h->generic_smem = sri::TiledSmem<16, 4>::total() * sizeof(double);
-            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_TRY(ensure_dynamic_smem(sri::tiled_kernel<16, 4, true>, h->device, h->generic_smem));
             SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::tiled_kernel<16, 4, true>, 128, h->generic_smem));
         } else {
             h->generic_smem = sri::TiledSmem<32, 8>::total() * sizeof(double);
-            SRI_CUDA(cudaFuncSetAttribute(sri::tiled_kernel<32, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->generic_smem));
+            SRI_TRY(ensure_dynamic_smem(sri::tiled_kernel<32, 8, true>, h->device, h->generic_smem));
             SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->generic_blocks_per_sm, sri::tiled_kernel<32, 8, true>, 256, h->generic_smem));
         }
-        if (h->generic_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: generic kernel does not fit on this device"); }
+        if (h->generic_blocks_per_sm < 1) { return fail(SRI_ERR_CUDA, "sri_create: generic kernel does not fit on this device"); }
     }
     {
         std::vector<double> t(N);
@@ -728,11 +809,11 @@ int sri_create(int N, int device, sri_handle* out) {
         SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fused_blocks_per_sm, sri::fused16_kernel<0, true>, kFusedThreads, kFusedSmem));
         h->stage_blocks_per_sm = h->fused_blocks_per_sm;
     }
-    if (h->fused_blocks_per_sm < 1 || h->stage_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: kernel does not fit on this device"); }
+    if (h->fused_blocks_per_sm < 1 || h->stage_blocks_per_sm < 1) { return fail(SRI_ERR_CUDA, "sri_create: kernel does not fit on this device"); }
     if (N <= 16) {
         if (M == 15) SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::fused16_dmma_kernel<15>, sri::kDmmaThreads, sri::kDmmaSmem));
         else SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->dmma_blocks_per_sm, sri::fused16_dmma_kernel<0>, sri::kDmmaThreads, sri::kDmmaSmem));
-        if (h->dmma_blocks_per_sm < 1) { sri_destroy(h); return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
+        if (h->dmma_blocks_per_sm < 1) { return fail(SRI_ERR_CUDA, "sri_create: DMMA kernel does not fit on this device"); }
         // Both are sm_100a kernels of this library; SRI_FUSED16_IMPL=scalar selects the row-pivoting scalar kernel for
         // every rod (A/B measurements), the default is the DMMA elimination with the scalar kernel as its second pass.
     }
@@ -742,13 +823,28 @@ int sri_create(int N, int device, sri_handle* out) {
         if (const char* si = std::getenv("SRI_STAGE_IMPL")) h->stage_impl = std::strcmp(si, "tma") == 0 ? 1 : (std::strcmp(si, "ldg") == 0 ? 2 : 0);
         if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
     }
+    return SRI_OK;
+    }();
+    if (rc != SRI_OK) {  // nothing allocated so far may leak: the context, its stream, the tables already uploaded
+        const std::string keep = g_last_error;
+        sri_destroy(h);
+        g_last_error = keep;
+        return rc;
+    }
     *out = h;
     return SRI_OK;
 }
 
 int sri_destroy(sri_handle h) {
     if (!h) return SRI_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard;
+    if (guard.enter(h) != SRI_OK) { delete h; return SRI_ERR_CUDA; }
+    if (h->nccl_comm) sri_nccl_finalize(h);
+    if (h->d_dnn) cudaFree(h->d_dnn);
+    if (h->d_gather) cudaFree(h->d_gather);
+    if (h->pipe_event) cudaEventDestroy(h->pipe_event);
+    if (h->newton.host_state) cudaFreeHost(h->newton.host_state);
+    for (cudaEvent_t e : h->newton.ev) if (e) cudaEventDestroy(e);
     if (h->d_ops16) cudaFree(h->d_ops16);
     if (h->d_ops2) cudaFree(h->d_ops2);
     if (h->d_tnodes) cudaFree(h->d_tnodes);
@@ -773,19 +869,19 @@ int sri_destroy(sri_handle h) {
 }
 
 int sri_set_stream(sri_handle h, void* cuda_stream) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     return SRI_OK;
 }
 
 int sri_reset_stream(sri_handle h) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     h->stream = h->own_stream;
     return SRI_OK;
 }
 
 int sri_synchronize(sri_handle h) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     SRI_CUDA(cudaStreamSynchronize(h->stream));
     return SRI_OK;
 }
@@ -813,30 +909,56 @@ int sri_get_operator(sri_handle h, int which, double* out) {
     return SRI_OK;
 }
 
+// device pointers, handle's device current
+static int strain_from_modes_dev(sri_context* h, int64_t batch, int ne, const double* dqe, double* dK) {
+    const long long total = (long long)batch * 3 * h->N;
+    if (ne <= 8) {
+        const long long rows = (long long)batch * 3;
+        if (h->N <= 16) strain_from_modes_table_kernel<16><<<(unsigned)((rows + 15) / 16), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK, h->skip);
+        else if (h->N <= 32) strain_from_modes_table_kernel<32><<<(unsigned)((rows + 7) / 8), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK, h->skip);
+        else strain_from_modes_table_kernel<64><<<(unsigned)((rows + 3) / 4), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK, h->skip);
+    } else {
+        strain_from_modes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, dqe, dK, h->skip);
+    }
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
 int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe, double* K) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || ne < 1 || (batch > 0 && (!qe || !K))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_strain_from_modes: bad arguments");
     if (batch == 0) return SRI_OK;
     Staging st(h);
     const double* dqe; double* dK;
     SRI_TRY(st.in(qe, (size_t)batch * 3 * ne, &dqe));
     SRI_TRY(st.out(K, (size_t)batch * 3 * h->N, &dK));
-    const long long total = (long long)batch * 3 * h->N;
-    if (ne <= 8) {
-        const long long rows = (long long)batch * 3;
-        if (h->N <= 16) strain_from_modes_table_kernel<16><<<(unsigned)((rows + 15) / 16), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK);
-        else if (h->N <= 32) strain_from_modes_table_kernel<32><<<(unsigned)((rows + 7) / 8), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK);
-        else strain_from_modes_table_kernel<64><<<(unsigned)((rows + 3) / 4), 256, 0, h->stream>>>(rows, h->N, ne, h->d_ptab, dqe, dK);
-    } else {
-        strain_from_modes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(batch, h->N, ne, h->d_tnodes, dqe, dK);
+    SRI_TRY(strain_from_modes_dev(h, batch, ne, dqe, dK));
+    return st.finish();
+}
+
+int sri_assemble_A(sri_handle h, int64_t batch, const double* K, double* A_NN) {
+    SRI_ENTER(h);
+    if (batch < 0 || (batch > 0 && (!K || !A_NN))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_assemble_A: bad arguments");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M, n = 4 * M;
+    if (!h->d_dnn) {
+        SRI_CUDA(cudaMalloc(&h->d_dnn, sizeof(double) * M * M));
+        SRI_CUDA(cudaMemcpy(h->d_dnn, h->ops.Dn_NN.data(), sizeof(double) * M * M, cudaMemcpyHostToDevice));
     }
+    Staging st(h);
+    const double* dK; double* dA;
+    SRI_TRY(st.in(K, (size_t)batch * 3 * N, &dK));
+    SRI_TRY(st.out(A_NN, (size_t)batch * n * n, &dA));
+    const long long cap = (long long)h->sm_count * 8;
+    assemble_A_kernel<<<(unsigned)(batch < cap ? batch : cap), 256, 0, h->stream>>>(batch, N, h->d_dnn, dK, dA);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return st.finish();
 }
 
 int sri_integrate_all(sri_handle h, const sri_rod_batch* rods) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (!rods) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: rods == NULL");
     const int64_t B = rods->batch;
     if (B < 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all: negative batch");
@@ -863,7 +985,9 @@ int sri_integrate_all(sri_handle h, const sri_rod_batch* rods) {
     SRI_TRY(st.out(rods->m, (size_t)B * 3 * M, &p.m));
     SRI_TRY(st.out(rods->info, (size_t)B, &p.info));
     SRI_TRY(launch_fused16<true>(h, p));
-    return st.finish();
+    SRI_TRY(st.finish());
+    if (rods->info && !is_device_pointer(rods->info)) return singular_status(rods->info, B, "sri_integrate_all");
+    return SRI_OK;
 }
 
 int sri_integrate_quaternions(sri_handle h, int64_t batch, const double* K, const double* q0, double* Q, int* info) {
@@ -874,7 +998,7 @@ int sri_integrate_quaternions(sri_handle h, int64_t batch, const double* K, cons
 }
 
 int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const double* Gamma, const double* r0, double* r) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!Q || !r))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_position: bad arguments");
     if (batch == 0) return SRI_OK;
     const int N = h->N, M = h->M;
@@ -891,7 +1015,7 @@ int sri_integrate_position(sri_handle h, int64_t batch, const double* Q, const d
 }
 
 int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const double* F_tip, double* n) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!F_tip || !n))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_stress: bad arguments");
     if (batch == 0) return SRI_OK;
     const int N = h->N, M = h->M;
@@ -916,7 +1040,7 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
 
 int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* Gamma,
                          const double* n, const double* lbar, const double* M_tip, double* m) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!Q || !n || !M_tip || !m))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_couple: bad arguments");
     if (batch == 0) return SRI_OK;
     const int N = h->N, M = h->M;
@@ -939,7 +1063,7 @@ int sri_integrate_couple(sri_handle h, int64_t batch, const double* Q, const dou
 int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const double* K0, const double* H_diag,
                        const double* Q, const double* q0, const double* m, const double* M_tip, double* rho,
                        double* norm2_and_max) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!K || !H_diag || !Q || !m || !M_tip))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_shape_residual: bad arguments");
     if (batch == 0) return SRI_OK;
     const int N = h->N, M = h->M;
@@ -968,7 +1092,7 @@ int sri_shape_residual(sri_handle h, int64_t batch, const double* K, const doubl
 
 int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double* q0, const double* n, const double* m,
                      const double* F_tip, const double* M_tip, double* Lambda) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!Q || !n || !m || !F_tip || !M_tip || !Lambda))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_wrench_local: bad arguments");
     if (batch == 0) return SRI_OK;
     const int N = h->N, M = h->M;
@@ -991,7 +1115,7 @@ int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double*
 int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, const double* Q, const double* q0,
                                const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
                                const double* M_tip, double* Lambda, int* info) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!K || !Q || !F_tip || !M_tip || !Lambda))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_wrench_local: bad arguments");
     if (h->N > 16) return fail(SRI_ERR_UNSUPPORTED_N, "sri_integrate_wrench_local: N <= 16 (use sri_wrench_local on the global-frame stages for larger N)");
     if (batch == 0) return SRI_OK;
@@ -1009,42 +1133,25 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &p.Lambda));
     SRI_TRY(st.out(info, (size_t)batch, &p.info));
-    if (!h->wrench_configured) {
-        SRI_CUDA(cudaFuncSetAttribute(sri::wrench_local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sri::kWrenchSmem));
-        h->wrench_configured = true;
-    }
+    SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_kernel, h->device, sri::kWrenchSmem));
     const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
     const long long cap = (long long)h->sm_count;  // one CTA of 8 warps per SM (24 KB of shared memory per rod)
     sri::wrench_local_solve_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchWarps, sri::kWrenchSmem, h->stream>>>(p);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
-    return st.finish();
+    SRI_TRY(st.finish());
+    if (info && !is_device_pointer(info)) return singular_status(info, batch, "sri_integrate_wrench_local");
+    return SRI_OK;
 }
 
-int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, const double* K0, const double* H_diag,
-                          const double* Q, const double* q0, const double* m, const double* M_tip, double* g,
-                          double* norm2_and_max) {
-    SRI_TRY(check_handle(h));
-    if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!K || !H_diag || !Q || !m || !M_tip || !g)))
-        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_galerkin_residual: bad arguments (1 <= ne <= 8)");
-    if (batch == 0) return SRI_OK;
-    const int N = h->N, M = h->M;
-    double H[3];
-    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
-    else std::memcpy(H, H_diag, sizeof(H));
-    Staging st(h);
-    const double *dK, *dK0, *dQ, *dq0, *dm, *dMt; double* dg; double* dred = nullptr;
-    SRI_TRY(st.in(K, (size_t)batch * 3 * N, &dK));
-    SRI_TRY(st.in(K0, (size_t)batch * 3 * N, &dK0));
-    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
-    SRI_TRY(st.in(q0, (size_t)batch * 4, &dq0));
-    SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
-    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
-    SRI_TRY(st.out(g, (size_t)batch * 3 * ne, &dg));
+// device pointers, H on the host, handle's device current
+static int galerkin_residual_dev(sri_context* h, int64_t batch, int ne, const double* dK, const double* dK0, const double* H,
+                                 const double* dQ, const double* dq0, const double* dm, const double* dMt, double* dg,
+                                 double* dred) {
+    const int N = h->N;
     const int G = N <= 16 ? 16 : 32;
     const long long blocks = ((long long)batch * G + 255) / 256;
-    if (norm2_and_max) {
-        SRI_TRY(st.out(norm2_and_max, 2, &dred));
+    if (dred) {
         if (!h->d_counter) {
             SRI_CUDA(cudaMalloc(&h->d_counter, sizeof(unsigned)));
             SRI_CUDA(cudaMemset(h->d_counter, 0, sizeof(unsigned)));
@@ -1062,7 +1169,7 @@ int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, 
 #define SRI_GALERKIN(GG, NE_)                                                                                            \
     galerkin_residual_kernel<GG, NE_><<<(unsigned)blocks, 256, 0, h->stream>>>(batch, N, h->d_ptab, h->d_ccw, dK, dK0, H[0], \
                                                                                  H[1], H[2], dQ, dq0, dm, dMt, dg,          \
-                                                                                 h->d_partial, h->d_counter, dred)
+                                                                                 h->d_partial, h->d_counter, dred, h->skip)
 #define SRI_GALERKIN_NE(GG)                                                                                              \
     switch (ne) {                                                                                                        \
         case 1: SRI_GALERKIN(GG, 1); break; case 2: SRI_GALERKIN(GG, 2); break; case 3: SRI_GALERKIN(GG, 3); break;      \
@@ -1074,11 +1181,36 @@ int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, 
 #undef SRI_GALERKIN
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+int sri_galerkin_residual(sri_handle h, int64_t batch, int ne, const double* K, const double* K0, const double* H_diag,
+                          const double* Q, const double* q0, const double* m, const double* M_tip, double* g,
+                          double* norm2_and_max) {
+    SRI_ENTER(h);
+    if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!K || !H_diag || !Q || !m || !M_tip || !g)))
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_galerkin_residual: bad arguments (1 <= ne <= 8)");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M;
+    double H[3];
+    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
+    else std::memcpy(H, H_diag, sizeof(H));
+    Staging st(h);
+    const double *dK, *dK0, *dQ, *dq0, *dm, *dMt; double* dg; double* dred = nullptr;
+    SRI_TRY(st.in(K, (size_t)batch * 3 * N, &dK));
+    SRI_TRY(st.in(K0, (size_t)batch * 3 * N, &dK0));
+    SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
+    SRI_TRY(st.in(q0, (size_t)batch * 4, &dq0));
+    SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
+    SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
+    SRI_TRY(st.out(g, (size_t)batch * 3 * ne, &dg));
+    if (norm2_and_max) SRI_TRY(st.out(norm2_and_max, 2, &dred));
+    SRI_TRY(galerkin_residual_dev(h, batch, ne, dK, dK0, H, dQ, dq0, dm, dMt, dg, dred));
     return st.finish();
 }
 
 int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f, double* out) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!f || !out))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_project_onto_modes: bad arguments (1 <= ne <= 8)");
     if (batch == 0) return SRI_OK;
     Staging st(h);
@@ -1093,7 +1225,7 @@ int sri_project_onto_modes(sri_handle h, int64_t batch, int ne, const double* f,
 }
 
 int sri_generalised_forces(sri_handle h, int64_t batch, int ne, const double* Lambda, double* Qad) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || ne < 1 || ne > 8 || (batch > 0 && (!Lambda || !Qad))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_generalised_forces: bad arguments (1 <= ne <= 8)");
     if (batch == 0) return SRI_OK;
     Staging st(h);
@@ -1107,16 +1239,10 @@ int sri_generalised_forces(sri_handle h, int64_t batch, int ne, const double* La
     return st.finish();
 }
 
-int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* Q, const double* q0,
-                       const double* Gamma, const double* n, const double* m, const double* M_tip, double* J) {
-    SRI_TRY(check_handle(h));
-    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || (batch > 0 && (!Q || !n || !m || !M_tip || !J)))
-        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_shape_jacobian: bad arguments (1 <= ne <= 8)");
-    if (batch == 0) return SRI_OK;
-    const int N = h->N, M = h->M, nq = 3 * ne;
-    double H[3];
-    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
-    else std::memcpy(H, H_diag, sizeof(H));
+// device pointers, H on the host, handle's device current
+static int shape_jacobian_dev(sri_context* h, int64_t batch, int ne, const double* H, const double* dQ, const double* dq0,
+                              const double* dG, const double* dn, const double* dm, const double* dMt, double* dJ) {
+    const int N = h->N, M = h->M;
     if (!h->d_jac) {
         std::vector<double> t((size_t)2 * M * M);
         for (int i = 0; i < M; ++i)
@@ -1129,10 +1255,25 @@ int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag
     }
     constexpr int kWarps = 4;
     const size_t smem = ((size_t)2 * M * M + (size_t)9 * N + (size_t)kWarps * JacobianScratch::total(N)) * sizeof(double);
-    if (!h->jac_configured) {
-        if (smem > 48 * 1024) SRI_CUDA(cudaFuncSetAttribute(shape_jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->jac_configured = true;
-    }
+    SRI_TRY(ensure_dynamic_smem(shape_jacobian_kernel, h->device, smem));
+    const long long want = (batch + kWarps - 1) / kWarps, cap = (long long)h->sm_count * 8;
+    shape_jacobian_kernel<<<(unsigned)(want < cap ? want : cap), 32 * kWarps, smem, h->stream>>>(
+        batch, N, ne, h->d_jac, h->d_jac + (size_t)M * M, h->d_ptab, h->d_ccw, H[0], H[1], H[2], dQ, dq0, dG, dn, dm, dMt, dJ, h->skip);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* Q, const double* q0,
+                       const double* Gamma, const double* n, const double* m, const double* M_tip, double* J) {
+    SRI_ENTER(h);
+    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || (batch > 0 && (!Q || !n || !m || !M_tip || !J)))
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_shape_jacobian: bad arguments (1 <= ne <= 8)");
+    if (batch == 0) return SRI_OK;
+    const int N = h->N, M = h->M, nq = 3 * ne;
+    double H[3];
+    if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
+    else std::memcpy(H, H_diag, sizeof(H));
     Staging st(h);
     const double *dQ, *dq0, *dG, *dn, *dm, *dMt; double* dJ;
     SRI_TRY(st.in(Q, (size_t)batch * 4 * M, &dQ));
@@ -1142,60 +1283,177 @@ int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag
     SRI_TRY(st.in(m, (size_t)batch * 3 * M, &dm));
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &dMt));
     SRI_TRY(st.out(J, (size_t)batch * nq * nq, &dJ));
-    const long long want = (batch + kWarps - 1) / kWarps, cap = (long long)h->sm_count * 8;
-    shape_jacobian_kernel<<<(unsigned)(want < cap ? want : cap), 32 * kWarps, smem, h->stream>>>(
-        batch, N, ne, h->d_jac, h->d_jac + (size_t)M * M, h->d_ptab, h->d_ccw, H[0], H[1], H[2], dQ, dq0, dG, dn, dm, dMt, dJ);
-    g_launches.fetch_add(1);
-    SRI_CUDA(cudaGetLastError());
+    SRI_TRY(shape_jacobian_dev(h, batch, ne, H, dQ, dq0, dG, dn, dm, dMt, dJ));
     return st.finish();
 }
 
-int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const double* b, double* x, int* info) {
-    SRI_TRY(check_handle(h));
-    if (batch < 0 || n < 1 || n > 24 || (batch > 0 && (!A || !b || !x))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: bad arguments (1 <= n <= 24)");
-    if (batch == 0) return SRI_OK;
-    for (const void* p : {(const void*)A, (const void*)b, (const void*)x, (const void*)info})
-        if (p && !is_device_pointer(p)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: device pointers only");
+static int solve_small_dev(sri_context* h, int64_t batch, int n, double* A, const double* b, double* x, int* info) {
     const int T = n <= 13 ? 128 : (n <= 19 ? 64 : 32);
     const size_t smem = (size_t)(n * n + n) * (T + 1) * sizeof(double);
-    if (!h->solve_small_configured) {
-        SRI_CUDA(cudaFuncSetAttribute(solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        h->solve_small_configured = true;
-    }
-    solve_small_kernel<<<(unsigned)((batch + T - 1) / T), T, smem, h->stream>>>(batch, n, A, b, x, info);
+    SRI_TRY(ensure_dynamic_smem(solve_small_kernel, h->device, smem));
+    solve_small_kernel<<<(unsigned)((batch + T - 1) / T), T, smem, h->stream>>>(batch, n, A, b, x, info, h->skip);
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     return SRI_OK;
 }
 
-// Newton iteration of the static shape problem, host loop in this library (no torch, no Python in the loop): per iteration
-// one hot-path call on the 3 ne forward-difference copies of the batch, the fused Galerkin residual, the per-rod solve
-// and one 16-byte read of the norms.  rod_modeling.pdf section 2.2; BASELINE configs[4].
+int sri_solve_small_batched(sri_handle h, int64_t batch, int n, double* A, const double* b, double* x, int* info) {
+    SRI_ENTER(h);
+    if (batch < 0 || n < 1 || n > 24 || (batch > 0 && (!A || !b || !x))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: bad arguments (1 <= n <= 24)");
+    if (batch == 0) return SRI_OK;
+    for (const void* p : {(const void*)A, (const void*)b, (const void*)x, (const void*)info})
+        if (p && !is_device_pointer(p)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_solve_small_batched: device pointers only");
+    return solve_small_dev(h, batch, n, A, b, x, info);
+}
+
+// ---- NCCL, bound at run time --------------------------------------------------------------------------------------
+// The library does not link against NCCL: libnccl.so.2 is opened with dlopen when sri_nccl_* is first called (inside a
+// PyTorch process that resolves to the copy torch has already loaded).  Only the five entry points below are used.
+namespace {
+struct NcclUniqueId { char internal[128]; };  // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclDouble = 8;  // ncclFloat64
+
+int nccl_api(NcclApi** out) {
+    static std::mutex mu;
+    static NcclApi api;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!api.lib) {
+        void* lib = nullptr;
+        if (const char* path = std::getenv("SRI_NCCL_LIB")) lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return fail(SRI_ERR_CUDA, std::string("NCCL is not available: ") + (dlerror() ? dlerror() : "dlopen(libnccl.so.2) failed"));
+        NcclApi a;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(lib, "ncclAllGather"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GetErrorString) {
+            dlclose(lib);
+            return fail(SRI_ERR_CUDA, "NCCL library lacks an expected symbol");
+        }
+        a.lib = lib;
+        api = a;
+    }
+    *out = &api;
+    return SRI_OK;
+}
+#define SRI_NCCL(api, expr)                                                                                   \
+    do {                                                                                                      \
+        const int r__ = (expr);                                                                               \
+        if (r__ != 0) return fail(SRI_ERR_CUDA, std::string(#expr) + ": " + (api)->GetErrorString(r__));      \
+    } while (0)
+
+// all-gathers the 2 doubles at `red` of every rank into h->d_gather (rank-major) on the handle's stream; without a
+// communicator the "gather" is a 16-byte device copy
+int gather_norms(sri_context* h, const double* red) {
+    if (!h->d_gather) SRI_CUDA(cudaMalloc(&h->d_gather, sizeof(double) * 2 * std::max(1, h->nccl_nranks)));
+    if (h->nccl_comm) {
+        NcclApi* api = nullptr;
+        SRI_TRY(nccl_api(&api));
+        SRI_NCCL(api, api->AllGather(red, h->d_gather, 2, kNcclDouble, h->nccl_comm, h->stream));
+    } else {
+        SRI_CUDA(cudaMemcpyAsync(h->d_gather, red, 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return SRI_OK;
+}
+}  // namespace
+
+int sri_nccl_unique_id(void* id128) {
+    if (!id128) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_nccl_unique_id: null argument");
+    NcclApi* api = nullptr;
+    SRI_TRY(nccl_api(&api));
+    NcclUniqueId id;
+    SRI_NCCL(api, api->GetUniqueId(&id));
+    std::memcpy(id128, id.internal, sizeof(id.internal));
+    return SRI_OK;
+}
+
+int sri_nccl_init(sri_handle h, int nranks, int rank, const void* id128) {
+    SRI_ENTER(h);
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_nccl_init: bad arguments");
+    if (h->nccl_comm) SRI_TRY(sri_nccl_finalize(h));
+    NcclApi* api = nullptr;
+    SRI_TRY(nccl_api(&api));
+    NcclUniqueId id;
+    std::memcpy(id.internal, id128, sizeof(id.internal));
+    void* comm = nullptr;
+    SRI_NCCL(api, api->CommInitRank(&comm, nranks, id, rank));
+    h->nccl_comm = comm; h->nccl_nranks = nranks; h->nccl_rank = rank;
+    if (h->d_gather) { SRI_CUDA(cudaFree(h->d_gather)); h->d_gather = nullptr; }
+    return SRI_OK;
+}
+
+int sri_nccl_finalize(sri_handle h) {
+    SRI_ENTER(h);
+    if (!h->nccl_comm) return SRI_OK;
+    NcclApi* api = nullptr;
+    SRI_TRY(nccl_api(&api));
+    SRI_CUDA(cudaStreamSynchronize(h->stream));
+    void* comm = h->nccl_comm;
+    h->nccl_comm = nullptr; h->nccl_nranks = 1; h->nccl_rank = 0;
+    if (h->d_gather) { cudaFree(h->d_gather); h->d_gather = nullptr; }
+    SRI_NCCL(api, api->CommDestroy(comm));
+    return SRI_OK;
+}
+
+int sri_nccl_allreduce_norms(sri_handle h, double* norm2_and_max) {
+    SRI_ENTER(h);
+    if (!norm2_and_max || !is_device_pointer(norm2_and_max)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_nccl_allreduce_norms: device pointer required");
+    SRI_TRY(gather_norms(h, norm2_and_max));
+    fold_norms_kernel<<<1, 32, 0, h->stream>>>(h->d_gather, std::max(1, h->nccl_nranks), norm2_and_max);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
+    return SRI_OK;
+}
+
+// Newton iteration of the static shape problem, host loop in this library (no torch, no Python in the loop).  Per
+// iteration: Jacobian (analytic: one kernel; forward differences: ONE hot-path call on the 3 ne perturbed copies of the
+// batch), per-rod solve, update, re-evaluation (modal adapter, fused four-stage integration, Galerkin residual + norms),
+// then the convergence test.  rod_modeling.pdf section 2.2; BASELINE configs[4].
+//
+// reduce == NULL (device-side reduction): the norms are all-gathered over the handle's NCCL communicator on its stream
+// (or copied, single rank), newton_check_kernel turns them into a device-side `done` flag, and the host enqueues
+// iteration k+1 BEFORE it waits for the 16 bytes of iteration k (pinned mirror + event): the test lags by one iteration
+// and the GPU never idles on the host.  Kernels enqueued after convergence see the flag and exit, so qe, the iteration
+// count and the history are exactly those of the unlagged loop.
+// reduce != NULL: the caller's host callback reduces the norms; the loop synchronises once per iteration.
 int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* F_tip,
                             const double* M_tip, const double* K0, double* qe, double tol, int max_iter, double fd_step,
                             int64_t total_dof, sri_allreduce_fn reduce, void* reduce_ctx, sri_newton_report* report) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || ne < 1 || ne > 8 || !H_diag || max_iter < 0 || max_iter > 62 || !(fd_step >= 0.0) ||
         (batch > 0 && (!F_tip || !M_tip || !qe)))
         return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: bad arguments (1 <= ne <= 8, 0 <= max_iter <= 62, fd_step >= 0)");
     const bool analytic = fd_step == 0.0;  // Jacobian from sri_shape_jacobian instead of forward differences
+    const bool lagged = reduce == nullptr;
     const int N = h->N, M = h->M, n = 3 * ne;
     const int64_t B = batch, W = analytic ? 0 : (int64_t)n * B;
     double H[3];
     if (is_device_pointer(H_diag)) SRI_CUDA(cudaMemcpy(H, H_diag, sizeof(H), cudaMemcpyDeviceToHost));
     else std::memcpy(H, H_diag, sizeof(H));
     auto& ws = h->newton;
-    if (B > 0 && (ws.B != B || ws.ne != ne || ws.has_K0 != (K0 != nullptr) || ws.analytic != analytic)) {
+    if (ws.B != B || ws.ne != ne || ws.has_K0 != (K0 != nullptr) || ws.analytic != analytic || !ws.block) {
         SRI_CUDA(cudaStreamSynchronize(h->stream));
         if (ws.block) SRI_CUDA(cudaFree(ws.block));
         ws.block = nullptr; ws.B = -1;
         const bool k0 = K0 != nullptr;
         auto up = [](size_t v) { return (v + 1) & ~(size_t)1; };  // 16-byte aligned pieces
+        const size_t state_doubles = up((sizeof(NewtonState) + 7) / 8);
         const size_t sz[] = {up((size_t)3 * N * B), up((size_t)4 * M * B), up((size_t)3 * M * B), up((size_t)3 * M * B), up((size_t)n * B), up((size_t)n * n * B),
                              up((size_t)n * B), up((size_t)n * B), 8, up((size_t)3 * B), up((size_t)3 * B), k0 ? up((size_t)3 * N * B) : 0,
                              up((size_t)n * W), up((size_t)3 * N * W), up((size_t)4 * M * W), up((size_t)3 * M * W), up((size_t)n * W),
                              up((size_t)3 * W), up((size_t)3 * W), k0 ? up((size_t)3 * N * W) : 0};
-        size_t total = 0;
+        size_t total = state_doubles + up(((size_t)B + 1) / 2);
         for (size_t v : sz) total += v;
         SRI_CUDA(cudaMalloc(&ws.block, total * sizeof(double)));
         double** fields[] = {&ws.K, &ws.Q, &ws.m, &ws.nn, &ws.g0, &ws.J, &ws.delta, &ws.qe, &ws.red, &ws.F, &ws.Mt, &ws.K0,
@@ -1203,9 +1461,16 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         static_assert(sizeof(sz) / sizeof(sz[0]) == sizeof(fields) / sizeof(fields[0]), "one size per workspace field");
         size_t off = 0;
         for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) { *fields[i] = sz[i] ? ws.block + off : nullptr; off += sz[i]; }
+        ws.state = reinterpret_cast<NewtonState*>(ws.block + off); off += state_doubles;
+        ws.sinfo = reinterpret_cast<int*>(ws.block + off);
         ws.B = B; ws.ne = ne; ws.has_K0 = k0; ws.analytic = analytic;
     }
+    if (!ws.host_state) SRI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ws.host_state), sizeof(NewtonState)));
+    for (cudaEvent_t& e : ws.ev)
+        if (!e) SRI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaStream_t st = h->stream;
+    SRI_CUDA(cudaMemsetAsync(ws.state, 0, sizeof(NewtonState), st));
+    SRI_CUDA(cudaMemsetAsync(ws.red, 0, 2 * sizeof(double), st));  // a rank without rods contributes (0, 0)
     if (B > 0) {
         SRI_CUDA(cudaMemcpyAsync(ws.qe, qe, sizeof(double) * n * B, cudaMemcpyDefault, st));
         SRI_CUDA(cudaMemcpyAsync(ws.F, F_tip, sizeof(double) * 3 * B, cudaMemcpyDefault, st));
@@ -1217,51 +1482,98 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
             if (K0) SRI_CUDA(cudaMemcpyAsync(ws.K0w + (size_t)d * 3 * N * B, ws.K0, sizeof(double) * 3 * N * B, cudaMemcpyDeviceToDevice, st));
         }
     }
+    // every kernel launched from here on takes the device-side flag (lagged mode only); cleared on every way out
+    struct SkipScope { sri_context* h; ~SkipScope() { h->skip = nullptr; } } skip_scope{h};
+    h->skip = lagged ? &ws.state->done : nullptr;
+
     auto evaluate = [&](int64_t rods, const double* q, double* K, double* Q, double* m, const double* F, const double* Mt,
                         const double* k0, double* g, double* red, double* nout = nullptr) -> int {
-        SRI_TRY(sri_strain_from_modes(h, rods, ne, q, K));
-        sri_rod_batch rb{};
-        rb.batch = rods; rb.K = K; rb.F_tip = F; rb.M_tip = Mt; rb.Q = Q; rb.m = m; rb.n = nout;
-        SRI_TRY(sri_integrate_all(h, &rb));
-        return sri_galerkin_residual(h, rods, ne, K, k0, H, Q, nullptr, m, Mt, g, red);
+        SRI_TRY(strain_from_modes_dev(h, rods, ne, q, K));
+        sri::FusedParams p{};
+        p.batch = rods; p.N = N; p.M = M; p.ops = h->d_ops16;
+        p.K = K; p.F_tip = F; p.M_tip = Mt; p.Q = Q; p.m = m; p.n = nout;
+        SRI_TRY(launch_fused16<true>(h, p));
+        return galerkin_residual_dev(h, rods, ne, K, k0, H, Q, nullptr, m, Mt, g, red);
     };
-    sri_newton_report rep{};
+    // one Newton update + re-evaluation of the base point, all asynchronous on the handle's stream
+    auto iterate = [&]() -> int {
+        if (B == 0) return SRI_OK;
+        const long long tq = (long long)n * W, tj = (long long)B * n * n, tu = (long long)n * B;
+        if (analytic) {
+            SRI_TRY(shape_jacobian_dev(h, B, ne, H, ws.Q, nullptr, nullptr, ws.nn, ws.m, ws.Mt, ws.J));
+        } else {
+            fd_perturb_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.qe, ws.qw, h->skip);
+            g_launches.fetch_add(1);
+            SRI_TRY(evaluate(W, ws.qw, ws.Kw, ws.Qw, ws.mw, ws.Fw, ws.Mtw, ws.K0w, ws.gw, nullptr));
+            fd_jacobian_kernel<<<(unsigned)((tj + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.gw, ws.g0, ws.J, h->skip);
+            g_launches.fetch_add(1);
+        }
+        SRI_TRY(solve_small_dev(h, B, n, ws.J, ws.g0, ws.delta, ws.sinfo));
+        newton_update_kernel<<<(unsigned)((tu + 255) / 256), 256, 0, st>>>(B, n, ws.qe, ws.delta, ws.sinfo, ws.state, h->skip);
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+        return evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, analytic ? ws.nn : nullptr);
+    };
     const double dof = (double)(total_dof > 0 ? total_dof : (int64_t)n * B);
-    double* nbase = analytic ? ws.nn : nullptr;
-    if (B > 0) SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, nbase));
+    const int nranks = std::max(1, h->nccl_nranks);
+    // device-side convergence test number `t` and the asynchronous copy of its outcome to the pinned mirror
+    auto test = [&](int t) -> int {
+        SRI_TRY(gather_norms(h, ws.red));
+        newton_check_kernel<<<1, 32, 0, st>>>(h->d_gather, nranks, dof, tol, ws.state);
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+        SRI_CUDA(cudaMemcpyAsync(ws.host_state, ws.state, sizeof(NewtonState), cudaMemcpyDeviceToHost, st));
+        SRI_CUDA(cudaEventRecord(ws.ev[t & 1], st));
+        return SRI_OK;
+    };
+
+    sri_newton_report rep{};
+    if (B > 0) SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, analytic ? ws.nn : nullptr));
     rep.integrations = 1;
-    for (int it = 0;; ++it) {
-        double red[2] = {0.0, 0.0};
-        if (B > 0) {
+    unsigned long long singular = 0;
+    if (lagged) {
+        SRI_TRY(test(0));
+        for (int it = 0;; ++it) {
+            // enqueue iteration it+1 and its test before looking at test `it` (no-ops on the device if `it` converged)
+            if (it < max_iter) {
+                SRI_TRY(iterate());
+                SRI_TRY(test(it + 1));
+            }
+            // The mirror is overwritten by the copy of test it+1, which may already have run: every entry it holds is final
+            // once written (hist[t] never changes, done only rises), so reading after event `it` is safe either way.
+            SRI_CUDA(cudaEventSynchronize(ws.ev[it & 1]));
+            const volatile NewtonState* hs = ws.host_state;
+            const double s2 = hs->hist[it][0], mx = hs->hist[it][1];
+            rep.rms = dof > 0 ? std::sqrt(s2 / dof) : 0.0;
+            rep.max_abs = mx;
+            rep.rms_history[rep.history_len++] = rep.rms;
+            if (rep.rms < tol) { rep.converged = 1; break; }
+            if (it == max_iter) break;
+            rep.iterations += 1;
+            rep.integrations += analytic ? 1 : n + 1;
+        }
+        SRI_CUDA(cudaStreamSynchronize(st));
+        singular = ws.host_state->singular;  // the last copy has landed
+    } else {
+        for (int it = 0;; ++it) {
+            double red[2] = {0.0, 0.0};
             SRI_CUDA(cudaMemcpyAsync(red, ws.red, sizeof(red), cudaMemcpyDeviceToHost, st));
             SRI_CUDA(cudaStreamSynchronize(st));
+            if (reduce(red, reduce_ctx) != 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: the reduction callback failed");
+            rep.rms = dof > 0 ? std::sqrt(red[0] / dof) : 0.0;
+            rep.max_abs = red[1];
+            rep.rms_history[rep.history_len++] = rep.rms;
+            if (rep.rms < tol) { rep.converged = 1; break; }
+            if (it == max_iter) break;
+            SRI_TRY(iterate());
+            rep.iterations += 1;
+            rep.integrations += analytic ? 1 : n + 1;
         }
-        if (reduce && reduce(red, reduce_ctx) != 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape: the reduction callback failed");
-        rep.rms = dof > 0 ? std::sqrt(red[0] / dof) : 0.0;
-        rep.max_abs = red[1];
-        rep.rms_history[rep.history_len++] = rep.rms;
-        if (rep.rms < tol) { rep.converged = 1; break; }
-        if (it == max_iter) break;
-        if (B > 0) {
-            const long long tq = (long long)n * W, tj = (long long)B * n * n, tu = (long long)n * B;
-            if (analytic) {
-                SRI_TRY(sri_shape_jacobian(h, B, ne, H, ws.Q, nullptr, nullptr, ws.nn, ws.m, ws.Mt, ws.J));
-            } else {
-                fd_perturb_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.qe, ws.qw);
-                g_launches.fetch_add(1);
-                SRI_TRY(evaluate(W, ws.qw, ws.Kw, ws.Qw, ws.mw, ws.Fw, ws.Mtw, ws.K0w, ws.gw, nullptr));
-                fd_jacobian_kernel<<<(unsigned)((tj + 255) / 256), 256, 0, st>>>(B, n, fd_step, ws.gw, ws.g0, ws.J);
-                g_launches.fetch_add(1);
-            }
-            SRI_TRY(sri_solve_small_batched(h, B, n, ws.J, ws.g0, ws.delta, nullptr));
-            newton_update_kernel<<<(unsigned)((tu + 255) / 256), 256, 0, st>>>(tu, ws.qe, ws.delta);
-            g_launches.fetch_add(1);
-            SRI_CUDA(cudaGetLastError());
-            SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, nbase));
-        }
-        rep.iterations += 1;
-        rep.integrations += analytic ? 1 : n + 1;
+        SRI_CUDA(cudaMemcpyAsync(ws.host_state, ws.state, sizeof(NewtonState), cudaMemcpyDeviceToHost, st));
+        SRI_CUDA(cudaStreamSynchronize(st));
+        singular = ws.host_state->singular;
     }
+    rep.singular_solves = (int64_t)singular;
     if (B > 0) {
         SRI_CUDA(cudaMemcpyAsync(qe, ws.qe, sizeof(double) * n * B, cudaMemcpyDefault, st));
         SRI_CUDA(cudaStreamSynchronize(st));
@@ -1270,9 +1582,217 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
     return SRI_OK;
 }
 
+// ---- several devices in one process ------------------------------------------------------------------------------------
+
+}  // extern "C"
+
+struct sri_multi_context {
+    int N = 0;
+    std::vector<int> devices;
+    std::vector<sri_handle> handles;
+};
+
+namespace {
+
+// the rods [first, first + count) of a whole-batch description with HOST pointers
+sri_rod_batch shard_of(const sri_rod_batch& r, int N, int64_t first, int64_t count) {
+    const int M = N - 1;
+    sri_rod_batch s = r;
+    s.batch = count;
+    auto adv = [first](const double* p, size_t per_rod) { return p ? p + (size_t)first * per_rod : nullptr; };
+    auto advw = [first](double* p, size_t per_rod) { return p ? p + (size_t)first * per_rod : nullptr; };
+    s.K = adv(r.K, 3 * N); s.q0 = adv(r.q0, 4); s.r0 = adv(r.r0, 3); s.Gamma = adv(r.Gamma, 3 * N);
+    s.fbar = adv(r.fbar, 3 * N); s.lbar = adv(r.lbar, 3 * N); s.F_tip = adv(r.F_tip, 3); s.M_tip = adv(r.M_tip, 3);
+    s.Q = advw(r.Q, 4 * M); s.r = advw(r.r, 3 * M); s.n = advw(r.n, 3 * M); s.m = advw(r.m, 3 * M);
+    s.info = r.info ? r.info + first : nullptr;
+    return s;
+}
+
+// Runs fn(g) on one host thread per device and returns the first failure (its message becomes this thread's
+// sri_last_error_string; g_last_error is thread-local).
+template <typename Fn>
+int for_each_device(sri_multi_context* mh, Fn fn) {
+    const int G = (int)mh->handles.size();
+    std::vector<int> rc(G, SRI_OK);
+    std::vector<std::string> msg(G);
+    std::vector<std::thread> threads;
+    threads.reserve(G);
+    for (int g = 0; g < G; ++g)
+        threads.emplace_back([&, g]() {
+            rc[g] = fn(g);
+            if (rc[g] != SRI_OK) msg[g] = g_last_error;
+        });
+    for (auto& t : threads) t.join();
+    int worst = SRI_OK;
+    for (int g = 0; g < G; ++g)
+        if (rc[g] != SRI_OK && (worst == SRI_OK || worst == SRI_ERR_SINGULAR)) {  // a hard error outranks "some rod was singular"
+            worst = rc[g];
+            g_last_error = "device " + std::to_string(mh->devices[g]) + ": " + msg[g];
+        }
+    return worst;
+}
+
+// sum / max of the per-thread norms between the device threads of one process, added in shard order
+struct ThreadReduce {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 0, arrived = 0;
+    long generation = 0;
+    bool failed = false;
+    std::vector<double> parts;
+    double out[2] = {0.0, 0.0};
+};
+struct ThreadReduceCtx { ThreadReduce* red; int rank; };
+int thread_reduce_callback(double* v, void* ctx_) {
+    auto* ctx = static_cast<ThreadReduceCtx*>(ctx_);
+    ThreadReduce& R = *ctx->red;
+    std::unique_lock<std::mutex> lock(R.mu);
+    if (R.failed) return 1;
+    R.parts[2 * ctx->rank] = v[0];
+    R.parts[2 * ctx->rank + 1] = v[1];
+    if (++R.arrived == R.n) {
+        double s = 0.0, m = 0.0;
+        for (int r = 0; r < R.n; ++r) { s += R.parts[2 * r]; m = std::max(m, R.parts[2 * r + 1]); }
+        R.out[0] = s; R.out[1] = m;
+        R.arrived = 0;
+        ++R.generation;
+        R.cv.notify_all();
+    } else {
+        const long gen = R.generation;
+        R.cv.wait(lock, [&] { return R.generation != gen || R.failed; });
+        if (R.generation == gen) return 1;  // another shard failed
+    }
+    v[0] = R.out[0]; v[1] = R.out[1];
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sri_shard_range(int64_t total, int rank, int world, int64_t* first, int64_t* last) {
+    if (total < 0 || world < 1 || rank < 0 || rank >= world || !first || !last) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_shard_range: bad arguments");
+    // floor(rank * total / world) without overflow for any int64 total
+    auto cut = [&](int64_t r) { return (int64_t)(((__int128)r * (__int128)total) / world); };
+    *first = cut(rank);
+    *last = cut(rank + 1);
+    return SRI_OK;
+}
+
+int sri_device_count(int* ndev) {
+    if (!ndev) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_device_count: null argument");
+    *ndev = 0;
+    SRI_CUDA(cudaGetDeviceCount(ndev));
+    return SRI_OK;
+}
+
+int sri_create_multi(int N, const int* devices, int ndev, sri_multi_handle* out) {
+    if (!out) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create_multi: out == NULL");
+    *out = nullptr;
+    if (ndev < 1) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_create_multi: ndev must be >= 1");
+    sri_multi_context* mh = new (std::nothrow) sri_multi_context();
+    if (!mh) return fail(SRI_ERR_ALLOC, "sri_create_multi: out of host memory");
+    mh->N = N;
+    for (int g = 0; g < ndev; ++g) {
+        const int dev = devices ? devices[g] : g;
+        sri_handle h = nullptr;
+        const int rc = sri_create(N, dev, &h);
+        if (rc != SRI_OK) {
+            const std::string keep = g_last_error;
+            sri_destroy_multi(mh);
+            g_last_error = keep;
+            return rc;
+        }
+        mh->devices.push_back(dev);
+        mh->handles.push_back(h);
+    }
+    *out = mh;
+    return SRI_OK;
+}
+
+int sri_destroy_multi(sri_multi_handle mh) {
+    if (!mh) return SRI_OK;
+    for (sri_handle h : mh->handles) sri_destroy(h);
+    delete mh;
+    return SRI_OK;
+}
+
+int sri_multi_device_count(sri_multi_handle mh, int* ndev) {
+    if (!mh || !ndev) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_multi_device_count: null argument");
+    *ndev = (int)mh->handles.size();
+    return SRI_OK;
+}
+
+int sri_multi_get_handle(sri_multi_handle mh, int index, sri_handle* h) {
+    if (!mh || !h || index < 0 || index >= (int)mh->handles.size()) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_multi_get_handle: bad arguments");
+    *h = mh->handles[index];
+    return SRI_OK;
+}
+
+int sri_integrate_all_sharded(sri_multi_handle mh, const sri_rod_batch* rods) {
+    if (!mh || !rods) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all_sharded: null argument");
+    if (rods->batch < 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all_sharded: negative batch");
+    if (rods->batch == 0) return SRI_OK;
+    if (!all_host_pointers(rods)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all_sharded: host pointers only (use sri_integrate_all_per_device for resident data)");
+    const int G = (int)mh->handles.size();
+    return for_each_device(mh, [&](int g) -> int {
+        int64_t first = 0, last = 0;
+        SRI_TRY(sri_shard_range(rods->batch, g, G, &first, &last));
+        if (last == first) return SRI_OK;
+        const sri_rod_batch mine = shard_of(*rods, mh->N, first, last - first);
+        return sri_integrate_all(mh->handles[g], &mine);
+    });
+}
+
+int sri_integrate_all_per_device(sri_multi_handle mh, const sri_rod_batch* per_device) {
+    if (!mh || !per_device) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_all_per_device: null argument");
+    const int G = (int)mh->handles.size();
+    for (int g = 0; g < G; ++g)  // device buffers: every call returns as soon as its kernels are queued
+        if (per_device[g].batch > 0) SRI_TRY(sri_integrate_all(mh->handles[g], &per_device[g]));
+    for (int g = 0; g < G; ++g) SRI_TRY(sri_synchronize(mh->handles[g]));
+    return SRI_OK;
+}
+
+int sri_newton_static_shape_sharded(sri_multi_handle mh, int64_t batch, int ne, const double* H_diag, const double* F_tip,
+                                    const double* M_tip, const double* K0, double* qe, double tol, int max_iter,
+                                    double fd_step, sri_newton_report* report) {
+    if (!mh) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape_sharded: null handle");
+    if (batch < 0 || ne < 1 || ne > 8 || !H_diag || (batch > 0 && (!F_tip || !M_tip || !qe)))
+        return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape_sharded: bad arguments");
+    for (const void* p : {(const void*)H_diag, (const void*)F_tip, (const void*)M_tip, (const void*)K0, (const void*)qe})
+        if (p && is_device_pointer(p)) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_newton_static_shape_sharded: host pointers only");
+    const int G = (int)mh->handles.size(), N = mh->N, n = 3 * ne;
+    ThreadReduce red;
+    red.n = G;
+    red.parts.assign(2 * (size_t)G, 0.0);
+    std::vector<sri_newton_report> reps(G);
+    const int rc = for_each_device(mh, [&](int g) -> int {
+        int64_t first = 0, last = 0;
+        int r = sri_shard_range(batch, g, G, &first, &last);
+        ThreadReduceCtx ctx{&red, g};
+        if (r == SRI_OK)
+            r = sri_newton_static_shape(mh->handles[g], last - first, ne, H_diag, F_tip ? F_tip + 3 * first : nullptr,
+                                        M_tip ? M_tip + 3 * first : nullptr, K0 ? K0 + (size_t)3 * N * first : nullptr,
+                                        qe ? qe + (size_t)n * first : nullptr, tol, max_iter, fd_step, (int64_t)n * batch,
+                                        thread_reduce_callback, &ctx, &reps[g]);
+        if (r != SRI_OK) {  // release the shards waiting in the reduction
+            std::lock_guard<std::mutex> lock(red.mu);
+            red.failed = true;
+            red.cv.notify_all();
+        }
+        return r;
+    });
+    if (rc != SRI_OK) return rc;
+    if (report) {
+        *report = reps[0];
+        for (int g = 1; g < G; ++g) report->singular_solves += reps[g].singular_solves;
+    }
+    return SRI_OK;
+}
+
 int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t batch, double* K, double* F_tip,
                       double* M_tip, double* fbar) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (batch < 0 || first_rod < 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_generate_rods: bad arguments");
     if (batch == 0) return SRI_OK;
     for (const void* p : {(const void*)K, (const void*)F_tip, (const void*)M_tip, (const void*)fbar})
@@ -1284,7 +1804,7 @@ int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t ba
 }
 
 int sri_get_handback_count(sri_handle h, int64_t* count) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (!count) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_handback_count: null argument");
     *count = 0;
     if (!h->use_dmma || !h->d_list[3]) return SRI_OK;
@@ -1323,13 +1843,13 @@ static int measure_peak(sri_handle h, bool tensor, double* tflops) {
 }
 
 int sri_measure_fp64_peak(sri_handle h, double* tflops) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (!tflops) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_measure_fp64_peak: null argument");
     return measure_peak(h, false, tflops);
 }
 
 int sri_measure_dmma_peak(sri_handle h, double* tflops) {
-    SRI_TRY(check_handle(h));
+    SRI_ENTER(h);
     if (!tflops) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_measure_dmma_peak: null argument");
     return measure_peak(h, true, tflops);
 }

@@ -114,4 +114,12 @@ __host__ __device__ inline double u01_from_bits(uint32_t hi, uint32_t lo) {
     return (double)v * (1.0 / 9007199254740992.0);
 }
 
+// Device-side state of one sri_newton_static_shape solve (reduce == NULL mode).
+struct NewtonState {
+    int done;             // set by newton_check_kernel once the tolerance is met: every later kernel of the solve exits at once
+    int tested;           // number of convergence tests that have run
+    unsigned long long singular;  // per-rod Newton systems with a zero pivot (their update was skipped), over all iterations
+    double hist[64][2];   // [test] = sum g^2 and max |g| over all ranks
+};
+
 }  // namespace sri

@@ -73,6 +73,7 @@ struct FusedParams {
     int* rod_list;
     int* rod_count;
     int growth_log;  // DMMA kernel: 2^20 log2(G^2), G = accepted sub-diagonal growth max_{i>k} |c_ik| / |c_kk|
+    const int* skip; // optional device flag: when set and non-zero the kernel exits at once (sri_newton_static_shape)
 };
 
 // Per-rod shared scratch (doubles).
@@ -287,6 +288,7 @@ __device__ __forceinline__ void contract16(const double* T, const double* v, int
 // (position / stress / couple), reading Q (and optionally n) produced by an earlier call.
 template <int MS, bool SOLVE>
 __global__ void __launch_bounds__(SRI_THREADS, SOLVE ? SRI_MINBLOCKS : 4) fused16_kernel(const FusedParams p) {
+    if (p.skip && *p.skip) return;  // Newton loop: the solve has already converged (device-side flag), nothing to do
     extern __shared__ __align__(16) double smem[];
     double* tab = smem;  // OpsLayout16::total doubles
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -113,6 +113,7 @@ __global__ void __maxnreg__(SRI_DMMA_MAXNREG) fused16_dmma_kernel(const FusedPar
 #else
 __global__ void __launch_bounds__(kDmmaThreads, SRI_DMMA_MINBLOCKS) fused16_dmma_kernel(const FusedParams p) {
 #endif
+    if (p.skip && *p.skip) return;  // Newton loop: the solve has already converged (device-side flag), nothing to do
     extern __shared__ __align__(16) double smem[];
     double* stx = smem;             // 256 doubles
     double* tabAS = smem + 256;     // 256

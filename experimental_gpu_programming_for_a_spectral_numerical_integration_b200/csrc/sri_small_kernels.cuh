@@ -16,7 +16,8 @@ namespace {
 
 // K[b][c][i] = sum_k P_k(t_i) qe[b][c*ne+k]   (Phi<3,ne>(x_i)*qe, main.cpp:69; Legendre recurrence of utilities.h:59)
 __global__ void strain_from_modes_kernel(long long batch, int N, int ne, const double* __restrict__ tnodes,
-                                         const double* __restrict__ qe, double* __restrict__ K) {
+                                         const double* __restrict__ qe, double* __restrict__ K, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = batch * 3 * N;
     if (idx >= total) return;
@@ -56,7 +57,9 @@ __global__ void legendre_table_kernel(int N, const double* __restrict__ tnodes, 
 template <int NL>
 __global__ void __launch_bounds__(256) strain_from_modes_table_kernel(long long rows /* batch*3 */, int N, int ne,
                                                                       const double* __restrict__ ptab,
-                                                                      const double* __restrict__ qe, double* __restrict__ K) {
+                                                                      const double* __restrict__ qe, double* __restrict__ K,
+                                                                      const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const int i = threadIdx.x & (NL - 1);
     const long long bc = (long long)blockIdx.x * (256 / NL) + (threadIdx.x / NL);
     if (bc >= rows || i >= N) return;
@@ -191,7 +194,9 @@ __global__ void __launch_bounds__(256, 4) galerkin_residual_kernel(long long bat
                                                                 const double* __restrict__ Q, const double* __restrict__ q0,
                                                                 const double* __restrict__ m, const double* __restrict__ M_tip,
                                                                 double* __restrict__ g, double* __restrict__ partial,
-                                                                unsigned* __restrict__ counter, double* __restrict__ red) {
+                                                                unsigned* __restrict__ counter, double* __restrict__ red,
+                                                                const int* __restrict__ skip) {
+    if (skip && *skip) return;
     constexpr int ne = NE;
     const int M = N - 1;
     const int lane = threadIdx.x & 31, sub = lane & (G - 1);
@@ -292,7 +297,8 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
                                                              const double* __restrict__ Q, const double* __restrict__ q0,
                                                              const double* __restrict__ Gamma, const double* __restrict__ nin,
                                                              const double* __restrict__ m, const double* __restrict__ M_tip,
-                                                             double* __restrict__ J) {
+                                                             double* __restrict__ J, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ __align__(16) double jsm[];
     const int M = N - 1, n = 3 * ne;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -386,7 +392,9 @@ __global__ void __launch_bounds__(128) shape_jacobian_kernel(long long batch, in
 
 // ---- Newton driver helpers (sri_newton_static_shape) ---------------------------------------------------------------
 // qw[d][b][j] = qe[b][j] + (j == d ? step : 0): the n forward-difference copies of the batch
-__global__ void fd_perturb_kernel(long long B, int n, double step, const double* __restrict__ qe, double* __restrict__ qw) {
+__global__ void fd_perturb_kernel(long long B, int n, double step, const double* __restrict__ qe, double* __restrict__ qw,
+                                  const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per = B * n;
     if (idx >= per * n) return;
@@ -399,7 +407,8 @@ __global__ void fd_perturb_kernel(long long B, int n, double step, const double*
 
 // J[b][i][d] = (gw[d][b][i] - g0[b][i]) / step
 __global__ void fd_jacobian_kernel(long long B, int n, double step, const double* __restrict__ gw,
-                                   const double* __restrict__ g0, double* __restrict__ J) {
+                                   const double* __restrict__ g0, double* __restrict__ J, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * n * n) return;
     const int d = (int)(idx % n);
@@ -407,15 +416,73 @@ __global__ void fd_jacobian_kernel(long long B, int n, double step, const double
     J[idx] = (gw[(long long)d * B * n + bi] - g0[bi]) / step;
 }
 
-__global__ void newton_update_kernel(long long total, double* __restrict__ qe, const double* __restrict__ delta) {
+using sri::NewtonState;
+
+// qe -= delta for the rods whose Newton system was regular; counts the others.
+__global__ void newton_update_kernel(long long B, int n, double* __restrict__ qe, const double* __restrict__ delta,
+                                     const int* __restrict__ sinfo, NewtonState* __restrict__ state,
+                                     const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < total) qe[idx] -= delta[idx];
+    if (idx >= B * n) return;
+    const long long b = idx / n;
+    if (sinfo && sinfo[b] != 0) {
+        if (state && idx == b * n) atomicAdd(&state->singular, 1ULL);
+        return;
+    }
+    qe[idx] -= delta[idx];
+}
+
+// Convergence test on the device: gathered[r] = (sum g^2, max |g|) of rank r, added in rank order (every rank computes the
+// same bits); records the pair and raises the flag when sqrt(sum / dof) < tol.
+__global__ void newton_check_kernel(const double* __restrict__ gathered, int nranks, double dof, double tol,
+                                    NewtonState* __restrict__ state) {
+    if (threadIdx.x != 0 || state->done) return;
+    double s = 0.0, m = 0.0;
+    for (int r = 0; r < nranks; ++r) { s += gathered[2 * r]; m = fmax(m, gathered[2 * r + 1]); }
+    const int t = state->tested;
+    if (t < 64) { state->hist[t][0] = s; state->hist[t][1] = m; }
+    state->tested = t + 1;
+    const double rms = dof > 0.0 ? sqrt(s / dof) : 0.0;
+    if (rms < tol) state->done = 1;
+}
+
+// in-place (sum, max) over the ranks of an all-gathered norm pair (sri_nccl_allreduce_norms)
+__global__ void fold_norms_kernel(const double* __restrict__ gathered, int nranks, double* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    double s = 0.0, m = 0.0;
+    for (int r = 0; r < nranks; ++r) { s += gathered[2 * r]; m = fmax(m, gathered[2 * r + 1]); }
+    out[0] = s; out[1] = m;
+}
+
+// A_NN = I4 (x) Dn_NN - 1/2 blockdiag A(K_i), column-major 4M x 4M per rod: updateA main.cpp:55-88 with the index map
+// row = r M + i, col = c M + i of main.cpp:80-81 and the 4 x 4 block of main.cpp:72-75.  One CTA per rod.
+__global__ void assemble_A_kernel(long long batch, int N, const double* __restrict__ Dnn_cm, const double* __restrict__ K,
+                                  double* __restrict__ A) {
+    const int M = N - 1, n = 4 * M;
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* k = K + b * 3 * N;
+        double* a = A + b * (long long)n * n;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int col = e / n, row = e - col * n;
+            const int r = row / M, i = row - r * M, c = col / M, j = col - c * M;
+            double v = (r == c) ? Dnn_cm[j * M + i] : 0.0;
+            if (i == j) {
+                const double k0 = k[i], k1 = k[N + i], k2 = k[2 * N + i];
+                // A(K) rows: (0,-k0,-k1,-k2), (k0,0,k2,-k1), (k1,-k2,0,k0), (k2,k1,-k0,0)
+                const double blk[4][4] = {{0.0, -k0, -k1, -k2}, {k0, 0.0, k2, -k1}, {k1, -k2, 0.0, k0}, {k2, k1, -k0, 0.0}};
+                v = v - 0.5 * blk[r][c];
+            }
+            a[e] = v;
+        }
+    }
 }
 
 // One thread per system: Gaussian elimination with partial pivoting.  The block's systems (contiguous in global memory)
 // are staged in shared memory element-major, a[e * (T + 1) + thread]: coalesced copies, conflict-free in both phases.
 __global__ void solve_small_kernel(long long batch, int n, const double* __restrict__ A, const double* __restrict__ b,
-                                   double* __restrict__ x, int* __restrict__ info) {
+                                   double* __restrict__ x, int* __restrict__ info, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ double ssm[];
     const int T = blockDim.x, LD = T + 1, tid = threadIdx.x, nn = n * n;
     const long long s0 = (long long)blockIdx.x * T;

@@ -45,6 +45,7 @@ template <int LPR, int H, bool SOLVE>
 __global__ void __launch_bounds__(32 * H, (LPR == 16 ? 3 : 1)) tiled_kernel(const FusedParams p) {
     using SM = TiledSmem<LPR, H>;
     constexpr int RPW = SM::RPW, ROWS = SM::ROWS, SC = SM::SC;
+    if (p.skip && *p.skip) return;  // Newton loop: the solve has already converged (device-side flag), nothing to do
     extern __shared__ __align__(16) double smem[];
     const OpsLayoutGeneric L{ROWS};
     double* tab = smem + SM::tab();

@@ -65,6 +65,7 @@ template <int RT, int CT, int W>
 __global__ void __launch_bounds__(32 * W, (W == 4 ? SRI_T32_MINBLOCKS : 1)) tiled_dmma_kernel(const FusedParams p) {
     using C = TiledDmmaCfg<RT, CT, W>;
     constexpr int NC = C::NC, QR = C::QR, RS = C::RS, KT = C::KT, MT = C::MT;
+    if (p.skip && *p.skip) return;  // Newton loop: the solve has already converged (device-side flag), nothing to do
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     if ((long long)blockIdx.x >= p.batch) return;

@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define SRI_VERSION_MAJOR 0
-#define SRI_VERSION_MINOR 1
+#define SRI_VERSION_MINOR 2
 
 typedef enum sri_status {
     SRI_OK = 0,
@@ -40,7 +40,9 @@ typedef enum sri_status {
     SRI_ERR_UNSUPPORTED_N = -2,
     SRI_ERR_CUDA = -3,
     SRI_ERR_ALLOC = -4,
-    SRI_ERR_SINGULAR = -5 /* at least one rod hit a zero pivot; see the info array */
+    SRI_ERR_SINGULAR = -5 /* at least one rod hit a zero / non-finite pivot: returned by calls with HOST buffers and a non-NULL
+                             info array, after every output (the info array included) has been written; calls with device
+                             buffers are asynchronous and report through info[] only */
 } sri_status;
 
 typedef struct sri_context* sri_handle;
@@ -77,6 +79,12 @@ int sri_get_operator(sri_handle h, int which, double* out);
 
 /* K = Phi<3,ne>(x_i) * qe at every node (main.cpp:69).  qe [batch][3*ne] -> K [batch][3][N]. */
 int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe, double* K);
+
+/* updateA()  main.cpp:55-88 on D_NN = I4 (x) Dn_NN (main.cpp:98,102): the assembled collocation operator of stage 1,
+ * A_NN = D_NN - 1/2 blockdiag A(K_i), as the reference holds it before A_NN.inverse() (main.cpp:113).  The integration
+ * kernels never form it (they eliminate the left-preconditioned quaternion system in registers); this entry point exists so
+ * that the operator itself can be inspected and checked.  K [batch][3][N] -> A_NN [batch][4M*4M], column-major per rod. */
+int sri_assemble_A(sri_handle h, int64_t batch, const double* K, double* A_NN);
 
 /* ---- the four integration stages ---------------------------------------------------------------------- */
 
@@ -126,6 +134,26 @@ typedef struct sri_rod_batch {
     int* info;           /* [batch] or NULL */
 } sri_rod_batch;
 int sri_integrate_all(sri_handle h, const sri_rod_batch* rods);
+
+/* ---- several devices in one process (one host thread and one stream per GPU, contiguous rod ranges) -------- */
+
+typedef struct sri_multi_context* sri_multi_handle;
+/* Number of CUDA devices visible to this process (so that a host without the CUDA headers can size its shard list). */
+int sri_device_count(int* ndev);
+/* One sri_handle per listed device (devices == NULL => devices 0..ndev-1).  Rods are independent: no collective. */
+int sri_create_multi(int N, const int* devices, int ndev, sri_multi_handle* out);
+int sri_destroy_multi(sri_multi_handle mh);
+int sri_multi_device_count(sri_multi_handle mh, int* ndev);
+/* The handle of the index-th device (owned by mh), e.g. to generate or keep rods resident per device. */
+int sri_multi_get_handle(sri_multi_handle mh, int index, sri_handle* h);
+/* Rod-index block of shard `rank` of `world`: [floor(rank*total/world), floor((rank+1)*total/world)). */
+int sri_shard_range(int64_t total, int rank, int world, int64_t* first, int64_t* last);
+/* sri_integrate_all over all devices of mh.  HOST pointers: shard g integrates its contiguous block of rods->batch rods,
+ * streamed through its device by its own host thread (pinned memory recommended); returns when every result has landed. */
+int sri_integrate_all_sharded(sri_multi_handle mh, const sri_rod_batch* rods);
+/* The same with data already resident: per_device[g] describes the rods of device g (device pointers on that device; batch
+ * may differ per device or be 0).  Launches on every device, then synchronises all of them. */
+int sri_integrate_all_per_device(sri_multi_handle mh, const sri_rod_batch* per_device);
 
 /* ---- static shape problem (rod_modeling.pdf eq. 1.25) ------------------------------------- */
 
@@ -192,8 +220,13 @@ int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag
  * analytic Jacobian of sri_shape_jacobian (one integration per iteration); per-rod solve, update; stops when
  * sqrt(sum g^2 / total_dof) < tol or after max_iter iterations (<= 62).  total_dof: number of unknowns over all ranks
  * (0 => batch*3*ne).  reduce (or NULL): called once per iteration with the 2 host doubles [sum g^2, max |g|] of this
- * rank's rods, must replace them by the sum / max over the ranks (e.g. MPI_Allreduce, ncclAllReduce + copy) and return 0
- * -- the only collective of the method; every rank must call with the same max_iter, also ranks with batch == 0. */
+ * rank's rods, must replace them by the sum / max over the ranks (e.g. MPI_Allreduce) and return 0 -- the only collective
+ * of the method; every rank must call with the same max_iter, also ranks with batch == 0.
+ * With reduce == NULL the norms are reduced ON THE DEVICE: over the communicator attached by sri_nccl_init (one
+ * ncclAllGather of 16 bytes per iteration on the handle's stream) or, without one, over this handle's rods only.  In that
+ * mode the convergence test is a kernel that sets a device-side flag, the host enqueues iteration k+1 before it reads the
+ * norms of iteration k (the test lags by one iteration, so the GPU never waits for the host), and every
+ * kernel of an iteration enqueued after convergence exits at once: iterates and counts are those of the unlagged loop. */
 typedef int (*sri_allreduce_fn)(double* norm2_and_max, void* ctx);
 typedef struct sri_newton_report {
     int iterations;        /* Newton updates taken */
@@ -202,10 +235,29 @@ typedef struct sri_newton_report {
     double rms, max_abs;   /* of the last residual, over all ranks */
     double rms_history[64];
     int history_len;
+    int64_t singular_solves; /* per-rod Newton systems found singular (zero pivot), summed over the iterations; those rods
+                                kept their qe in that iteration */
 } sri_newton_report;
 int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* F_tip,
                             const double* M_tip, const double* K0, double* qe, double tol, int max_iter, double fd_step,
                             int64_t total_dof, sri_allreduce_fn reduce, void* reduce_ctx, sri_newton_report* report);
+/* The same solve over all devices of mh from one host process: HOST pointers, rods sharded by index as in
+ * sri_integrate_all_sharded, one host thread per device, the norms reduced between the threads (no NCCL, no MPI). */
+int sri_newton_static_shape_sharded(sri_multi_handle mh, int64_t batch, int ne, const double* H_diag, const double* F_tip,
+                                    const double* M_tip, const double* K0, double* qe, double tol, int max_iter,
+                                    double fd_step, sri_newton_report* report);
+
+/* ---- NCCL residual-norm reduction (BASELINE configs[4]; SURVEY 8e: the only collective, Newton driver only) -----------
+ * libnccl.so.2 is opened at run time (dlopen), the library does not link against it.  One process per GPU:
+ *   rank 0: sri_nccl_unique_id(id)  ->  broadcast the 128 bytes by any means (MPI, torch.distributed, a file)
+ *   all   : sri_nccl_init(h, nranks, rank, id)          (collective: ncclCommInitRank on the handle's device)
+ * after which sri_newton_static_shape(h, ..., reduce = NULL, ...) reduces its norms over that communicator on the
+ * handle's stream.  sri_nccl_allreduce_norms is that reduction alone (norm2_and_max: 2 doubles on the device, in place:
+ * sum over ranks, max over ranks; asynchronous on the handle's stream). */
+int sri_nccl_unique_id(void* id128);
+int sri_nccl_init(sri_handle h, int nranks, int rank, const void* id128);
+int sri_nccl_finalize(sri_handle h);
+int sri_nccl_allreduce_norms(sri_handle h, double* norm2_and_max);
 
 /* Batched dense solve A x = b for small systems (n <= 24), partial pivoting, one rod per thread: the Newton step
  * of the static shape problem.  A [batch][n][n] row-major (may be overwritten), b [batch][n] -> x [batch][n].
@@ -227,8 +279,9 @@ const char* sri_last_error_string(void);
 int64_t sri_kernel_launch_count(void);
 /* N <= 16: the elimination runs on the FP64 tensor cores in static pivot order; a rod whose sub-diagonal growth
  * max_{i>k} |c_ik| / |c_kk| exceeds the accepted bound (4; environment SRI_DMMA_GROWTH at sri_create) is handed
- * back to the row-pivoting kernel inside the same call.  Returns how many rods of the most recent device-buffer
- * call on this handle took that second pass (synchronises the handle's stream).  0 for N > 16. */
+ * back to the row-pivoting kernel inside the same call; 17 <= N <= 64 works the same way with the multi-warp DMMA
+ * kernel.  Returns how many rods of the most recent device-buffer call on this handle took that second pass
+ * (synchronises the handle's stream); 0 when the handle runs the row-pivoting kernels only (SRI_FUSED16_IMPL=scalar). */
 int sri_get_handback_count(sri_handle h, int64_t* count);
 /* Runs the library's FP64 FMA peak probe on the handle's device and returns TFLOP/s (roofline denominator). */
 int sri_measure_fp64_peak(sri_handle h, double* tflops);

@@ -1,8 +1,8 @@
 // sri_reference_api.hpp -- the reference's C++ function surface on top of the C ABI (include/sri.h).
 //
 // A maintainer of aGotelli/experimental_gpu_programming_for_a_spectral_numerical_integration keeps calling
-//   ComputeChebyshevPoints<N>(), GetCoefficients_c<N>(), getDn<N>(), Phi<na,ne>(X), integrateQuaternions(),
-//   updatePositionb(Q_stack), integratePosition()
+//   ComputeChebyshevPoints<N>(), GetCoefficients_c<N>(), getDn<N>(), Phi<na,ne>(X), updateA(qe, A_NN, D_NN),
+//   integrateQuaternions(), updatePositionb(Q_stack), integratePosition()
 // exactly as main.cpp does, but links libsri_cuda.so instead of compiling the Eigen code.  Differences, all forced by
 // the absence of Eigen in the boundary: dense results come back as sri::ref::Matrix (column-major, Eigen's default
 // storage order, with operator()(i,j) and data()), and the global `qe` of main.cpp:17 is an explicit argument.
@@ -121,6 +121,32 @@ static const sri::ref::Matrix Phi(const double t_X, const double& t_begin = 0, c
     sri::ref::Matrix P(t_na, t_na * t_ne);
     sri::ref::check(sri_phi(t_na, t_ne, t_X, t_begin, t_end, P.data()), "sri_phi");
     return P;
+}
+
+// ---- main.cpp:55-88: A_NN(r M + i, c M + i) = D_NN(r M + i, c M + i) - 1/2 A(K_i)(r, c), K_i = Phi<na,ne>(x_i) qe --
+// Same call shape as the reference: the caller passes A_NN initialised to D_NN = I4 (x) Dn_NN (main.cpp:98,102) and gets
+// the node-diagonal entries overwritten; every other entry of A_NN is left as the caller set it.  The entries are computed
+// on the device (sri_assemble_A, which holds Dn_NN itself); D_NN must therefore be the matrix of main.cpp:98 -- its
+// node-diagonal entries are checked against the handle's operator and std::invalid_argument is thrown otherwise.
+template <unsigned int t_number_of_chebyshev_nodes = 16, unsigned int t_ne = 3>
+static void updateA(const std::array<double, 3 * t_ne>& t_qe, sri::ref::Matrix& A_NN, const sri::ref::Matrix& D_NN, int device = 0) {
+    constexpr int N = t_number_of_chebyshev_nodes, M = N - 1, n = 4 * M;
+    if (A_NN.rows() != n || A_NN.cols() != n || D_NN.rows() != n || D_NN.cols() != n)
+        throw std::invalid_argument("updateA: A_NN and D_NN must be 4(N-1) x 4(N-1)");
+    sri::ref::Handle h(N, device);
+    std::vector<double> K(3 * N), dnn(static_cast<std::size_t>(M) * M);
+    sri::ref::check(sri_get_operator(h.get(), 1, dnn.data()), "sri_get_operator");
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c)
+            for (int i = 0; i < M; ++i)
+                if (D_NN(r * M + i, c * M + i) != (r == c ? dnn[static_cast<std::size_t>(i) * M + i] : 0.0))
+                    throw std::invalid_argument("updateA: D_NN is not I4 (x) Dn_NN of getDn<N>()");
+    sri::ref::check(sri_strain_from_modes(h.get(), 1, t_ne, t_qe.data(), K.data()), "sri_strain_from_modes");
+    sri::ref::Matrix full(n, n);
+    sri::ref::check(sri_assemble_A(h.get(), 1, K.data(), full.data()), "sri_assemble_A");
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c)
+            for (int i = 0; i < M; ++i) A_NN(r * M + i, c * M + i) = full(r * M + i, c * M + i);
 }
 
 // ---- main.cpp:91-118 (the global qe of main.cpp:17 becomes the argument) ----------------------------------------

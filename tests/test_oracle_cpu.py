@@ -475,3 +475,42 @@ def test_jacobian_by_quadrature_agrees_with_the_exact_tangent(make_oracle, N, to
     _, J_exact = galerkin_residual_and_jacobian(o, qe, F, Mt, H, ne)
     J = jacobian_by_quadrature(o, qe, F, Mt, H, ne)
     assert np.abs(J - J_exact).max() <= tol * np.abs(J_exact).max()
+
+
+# ---- rod length (rod_modeling.pdf eq. 2.17) ---------------------------------------------------------------
+
+@pytest.mark.parametrize("N,ell", [(16, 0.4), (24, 3.0)])
+def test_rod_length_is_an_input_scaling(make_oracle, N, ell):
+    """Integrating a rod of length ell on the physical interval [0, ell] (differentiation matrix Dn / ell, nodes
+    ComputeChebyshevPoints<N, ell>) equals the unit-interval integration of (ell K, ell Gamma, ell fbar, ell lbar): the
+    equivalence the package's scale_for_length() helper relies on.  Independent numpy collocation vs the oracle."""
+    o = make_oracle(N)
+    M = N - 1
+    rng = np.random.default_rng(7)
+    x = o.chebyshev_points(1.0)
+    assert np.allclose(o.chebyshev_points(ell), ell * x, rtol=0, atol=1e-15 * ell)
+    K = (rng.uniform(-1.5, 1.5, size=(3, 1)) + rng.uniform(-1, 1, size=(3, 1)) * (2 * x - 1))[None]
+    Gam = np.array([1.0, 0.04, -0.03])[None, :, None] * np.ones((1, 3, N))
+    fb = rng.normal(size=(1, 3, 1)) * np.ones((1, 1, N)); lb = 0.2 * rng.normal(size=(1, 3, 1)) * np.ones((1, 1, N))
+    F = rng.uniform(-1, 1, size=(1, 3)); Mt = rng.uniform(-1, 1, size=(1, 3))
+    out = o.integrate_all(ell * K, F, Mt, Gamma=ell * Gam, fbar=ell * fb, lbar=ell * lb, explicit_inverse=False)
+    D = o.dn() / ell
+    A = np.kron(np.eye(4), D[:M, :M])
+    for i in range(M):
+        Ak = _A_of_K(K[0, :, i])
+        for r in range(4):
+            for c in range(4):
+                A[r * M + i, c * M + i] -= 0.5 * Ak[r, c]
+    Q = np.linalg.solve(A, -np.kron(np.array([1.0, 0, 0, 0]), D[:M, M]))
+    assert np.abs(Q - out["Q"][0].reshape(-1)).max() <= 1e-12
+    w, xq, y, z = np.concatenate([Q.reshape(4, M), np.array([[1.0], [0], [0], [0]])], axis=1)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (xq * y - w * z), 2 * (xq * z + w * y)],
+                  [2 * (xq * y + w * z), 1 - 2 * (xq * xq + z * z), 2 * (y * z - w * xq)],
+                  [2 * (xq * z - w * y), 2 * (y * z + w * xq), 1 - 2 * (xq * xq + y * y)]])
+    rp = np.einsum("ijn,jn->in", R, Gam[0])
+    r = np.linalg.solve(D[:M, :M], rp[:, :M].T)
+    n = np.linalg.solve(D[1:, 1:], -fb[0][:, 1:].T - np.outer(D[1:, 0], F[0]))
+    m = np.linalg.solve(D[1:, 1:], -(np.cross(rp[:, 1:].T, n) + lb[0][:, 1:].T) - np.outer(D[1:, 0], Mt[0]))
+    assert np.abs(r.T - out["r"][0]).max() <= 1e-12
+    assert np.abs(n.T - out["n"][0]).max() <= 1e-12 * max(1.0, np.abs(n).max())
+    assert np.abs(m.T - out["m"][0]).max() <= 1e-11 * max(1.0, np.abs(m).max())

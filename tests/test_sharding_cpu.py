@@ -20,6 +20,19 @@ def test_shard_ranges_tile_the_batch():
         shard_range(10, 2, 2)
 
 
+def test_c_abi_shard_range_equals_the_python_one():
+    """sri_shard_range (what a C/C++ host and sri_integrate_all_sharded use) cuts exactly where sharding.shard_range does;
+    pure host arithmetic, no GPU needed."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SriError
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import shard_range as c_shard_range
+    for total in (0, 1, 7, 1000, 10 ** 6 + 3, 2 ** 62 + 12345):
+        for world in (1, 2, 3, 8, 64):
+            for rank in range(world):
+                assert c_shard_range(total, rank, world) == shard_range(total, rank, world)
+    with pytest.raises(SriError):
+        c_shard_range(10, 2, 2)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -69,3 +82,4 @@ def test_two_rank_sharding_matches_single_rank(tmp_path):
     for p in parts:
         assert abs(p["red"][0] - (rho ** 2).sum()) <= 1e-12 * (rho ** 2).sum()
         assert p["red"][1] == np.abs(rho).max()
+    assert np.array_equal(parts[0]["red"], parts[1]["red"])  # one all-gather folded in rank order: identical bits everywhere
