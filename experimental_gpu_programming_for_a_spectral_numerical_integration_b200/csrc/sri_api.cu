@@ -22,6 +22,7 @@
 #include "sri_fused16.cuh"
 #include "sri_fused16_dmma.cuh"
 #include "sri_generic.cuh"
+#include "sri_jacobian_dmma.cuh"
 #include "sri_stage_dmma.cuh"
 #include "sri_stage_generic.cuh"
 #include "sri_stage_generic_tma.cuh"
@@ -80,6 +81,8 @@ struct sri_context {
     double* d_ptab = nullptr;    // Legendre polynomials at the nodes, P_k(2 x_i - 1), [8][N]
     double* d_jac = nullptr;     // S = Dn_NN^-1 and S_T = D_TT^-1, row-major [M][M] each (sri_shape_jacobian), built on first use
     double* d_dnn = nullptr;     // Dn_NN, column-major [M][M] (sri_assemble_A), built on first use
+    int jac_occ[9] = {};         // resident CTAs per SM of shape_jacobian_dmma_kernel<ne>
+    int jac_impl = 0;            // 0: DMMA kernel for N <= 16 (default), 1: SRI_JACOBIAN_IMPL=scalar everywhere (A/B measurements)
     const int* skip = nullptr;   // Newton loop with the device-side convergence flag: kernels launched while this is set take
                                  // it as their "already converged, do nothing" flag (NULL everywhere else)
     void* nccl_comm = nullptr;   // ncclComm_t attached by sri_nccl_init
@@ -821,6 +824,7 @@ int sri_create(int N, int device, sri_handle* out) {
         const char* impl = std::getenv("SRI_FUSED16_IMPL");
         h->use_dmma = !(impl && std::strcmp(impl, "scalar") == 0);
         if (const char* si = std::getenv("SRI_STAGE_IMPL")) h->stage_impl = std::strcmp(si, "tma") == 0 ? 1 : (std::strcmp(si, "ldg") == 0 ? 2 : 0);
+        if (const char* ji = std::getenv("SRI_JACOBIAN_IMPL")) h->jac_impl = std::strcmp(ji, "scalar") == 0 ? 1 : 0;
         if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
     }
     return SRI_OK;
@@ -1243,6 +1247,32 @@ int sri_generalised_forces(sri_handle h, int64_t batch, int ne, const double* La
 static int shape_jacobian_dev(sri_context* h, int64_t batch, int ne, const double* H, const double* dQ, const double* dq0,
                               const double* dG, const double* dn, const double* dm, const double* dMt, double* dJ) {
     const int N = h->N, M = h->M;
+    if (N <= 16 && h->jac_impl == 0) {
+        // two [16 x 16] x [16 x 9 ne] contractions + the projection on the FP64 tensor cores, one rod per warp
+        int occ = 0;
+        const long long want = (batch + sri::kJacWarps - 1) / sri::kJacWarps;
+#define SRI_JAC(NE_)                                                                                                        \
+    {                                                                                                                       \
+        const size_t smem = (256 + (size_t)sri::kJacWarps * sri::JacDmmaScratch<NE_>::total) * sizeof(double);              \
+        SRI_TRY(ensure_dynamic_smem(sri::shape_jacobian_dmma_kernel<NE_>, h->device, smem));                                \
+        if (h->jac_occ[NE_] == 0)                                                                                            \
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->jac_occ[NE_], sri::shape_jacobian_dmma_kernel<NE_>,   \
+                                                                   32 * sri::kJacWarps, smem));                              \
+        occ = h->jac_occ[NE_];                                                                                               \
+        if (occ < 1) return fail(SRI_ERR_CUDA, "sri_shape_jacobian: kernel does not fit on this device");                    \
+        const long long cap = (long long)h->sm_count * occ;                                                                 \
+        sri::shape_jacobian_dmma_kernel<NE_><<<(unsigned)(want < cap ? want : cap), 32 * sri::kJacWarps, smem, h->stream>>>( \
+            batch, N, h->d_ops16, h->d_ptab, h->d_ccw, H[0], H[1], H[2], dQ, dq0, dG, dn, dm, dMt, dJ, h->skip);             \
+    }
+        switch (ne) {
+            case 1: SRI_JAC(1) break; case 2: SRI_JAC(2) break; case 3: SRI_JAC(3) break; case 4: SRI_JAC(4) break;
+            case 5: SRI_JAC(5) break; case 6: SRI_JAC(6) break; case 7: SRI_JAC(7) break; default: SRI_JAC(8) break;
+        }
+#undef SRI_JAC
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+        return SRI_OK;
+    }
     if (!h->d_jac) {
         std::vector<double> t((size_t)2 * M * M);
         for (int i = 0; i < M; ++i)

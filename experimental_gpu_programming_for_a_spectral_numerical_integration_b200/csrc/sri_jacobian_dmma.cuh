@@ -1,0 +1,241 @@
+// sri_jacobian_dmma.cuh -- analytic Jacobian of the Galerkin shape residual (sri_shape_jacobian) on the FP64 tensor
+// cores, N <= 16, one rod per warp.
+//
+// Math (restated on the CPU in oracle/tangent.py): for a direction d = (c, k), dK = P_k(t) e_c,
+//     u_i   = P_k(t_i) R_i[:, c]                          i = 0..M-1 (the base node does not rotate)
+//     dth   = S u                                         S   = Dn_NN^-1   (nodes 0..M-1; 0 at the base)
+//     v_j   = -((dth_j x b_j) x n_j) = dth_j (b_j.n_j) - b_j (dth_j.n_j)     nodes j = 1..N-1, b = R Gamma
+//     dm    = S_T v                                       S_T = D_TT^-1    (nodes 1..N-1; 0 at the tip)
+//     drho_i= H dK_i - R_i^T (dm_i - dth_i x m_i)         all N nodes
+//     J[(c',k')][d] = sum_i w_i P_k'(t_i) drho_i[c'].
+// All 3 ne directions of a rod go through the two integration matrices at once: two [16 x 16] x [16 x 9 ne]
+// contractions and one [ne x 16] x [16 x 9 ne] projection = (2 x 2 + 1) x 4 x NT DMMA m8n8k4, NT = ceil(9 ne / 8)
+// (80 DMMAs per rod at ne = 3), where the scalar kernel it replaces (shape_jacobian_kernel, still used for N > 16) spent
+// 2 x 15 x 45 x 9 FMAs per rod in one-lane dot products.  Every B fragment is evaluated by the lane that owns it
+// directly from the warp's nodal scratch (rotation matrices, b, n, m, and the two intermediate fields dth, dm), so the
+// only shared-memory round trips are those two fields.
+//
+// Fragment layout of mma.sync.m8n8k4.f64 (rho = lane / 4, cp = lane % 4): A[row rho][k cp], B[k cp][col rho],
+// C[row rho][cols 2 cp, 2 cp + 1].
+#pragma once
+#include "sri_device.cuh"
+#include "sri_stage_dmma.cuh"  // dmma_m8n8k4, StageTables
+
+namespace sri {
+
+constexpr int kJacWarps = 4;
+#ifndef SRI_JAC_MINBLOCKS
+#define SRI_JAC_MINBLOCKS 3  // 168 registers: 12 warps per SM
+#endif
+
+template <int NE>
+struct JacDmmaScratch {  // doubles per warp
+    static constexpr int NT = (9 * NE + 7) / 8;       // column tiles of the 9 NE = 3 (components) x 3 NE (directions) columns
+    static constexpr int LD = 8 * NT + 2;             // row stride of the two field arrays (even: double2 stores)
+    static constexpr int R = 0;                       // [16][9]  rotation matrices by node, row-major
+    static constexpr int b = R + 144;                 // [16][3]  R Gamma
+    static constexpr int n = b + 48;                  // [16][3]  internal force by node (node 0 unused)
+    static constexpr int m = n + 48;                  // [16][3]  internal couple by node (node 0 = M_tip)
+    static constexpr int bn = m + 48;                 // [16]     b . n
+    static constexpr int th = bn + 16;                // [16][LD] dtheta by node, column 3 d + comp
+    static constexpr int dm = th + 16 * LD;           // [17][LD] dm by node (row 0 = tip = 0, row 16 = padding)
+    static constexpr int total = dm + 17 * LD;
+};
+
+template <int NE>
+__global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 1) shape_jacobian_dmma_kernel(
+    long long batch, int N, const double* __restrict__ ops, const double* __restrict__ ptab, const double* __restrict__ ccw,
+    double h0, double h1, double h2, const double* __restrict__ Q, const double* __restrict__ q0,
+    const double* __restrict__ Gamma, const double* __restrict__ nin, const double* __restrict__ min_,
+    const double* __restrict__ M_tip, double* __restrict__ J, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    using SC = JacDmmaScratch<NE>;
+    constexpr int NT = SC::NT, LD = SC::LD, ND = 3 * NE;  // ND directions, 3 ND columns
+    extern __shared__ __align__(16) double jsm[];
+    double* Ps = jsm;            // [8][16] Legendre table, zero beyond node N-1
+    double* Pw = jsm + 128;      // [8][16] w_i P_k(t_i)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* scr = jsm + 256 + warp * SC::total;
+    const int M = N - 1;
+    const int rho = lane >> 2, cp = lane & 3;
+
+    for (int e = threadIdx.x; e < 128; e += blockDim.x) {
+        const int k = e >> 4, i = e & 15;
+        const double pv = i < N ? ptab[k * N + i] : 0.0;
+        Ps[e] = pv;
+        Pw[e] = i < N ? ccw[i] * pv : 0.0;
+    }
+    for (int e = lane; e < SC::total; e += 32) scr[e] = 0.0;
+    __syncthreads();
+
+    // A fragments, loaded once: the two integration matrices (zero padded 16 x 16, row-major) and the projection
+    double aS[2][4], aT[2][4], aP[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            aS[mt][kt] = ops[StageTables::Srm + (8 * mt + rho) * 16 + 4 * kt + cp];
+            aT[mt][kt] = ops[StageTables::STrm + (8 * mt + rho) * 16 + 4 * kt + cp];
+        }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) aP[kt] = rho < NE ? Pw[rho * 16 + 4 * kt + cp] : 0.0;
+
+    // per column tile: what this lane's B column (8 nt + rho) means
+    //   contractions: column = 3 d + comp          projection: column = c' ND + d
+    int colD[NT], colComp[NT], prjC[NT], prjD[NT];
+    bool colOk[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int col = 8 * nt + rho;
+        colOk[nt] = col < 3 * ND;
+        const int cc = colOk[nt] ? col : 0;
+        colD[nt] = cc / 3; colComp[nt] = cc - 3 * colD[nt];
+        prjC[nt] = cc / ND; prjD[nt] = cc - ND * prjC[nt];
+    }
+
+    double* Rs = scr + SC::R; double* bs = scr + SC::b; double* ns = scr + SC::n; double* ms = scr + SC::m;
+    double* bns = scr + SC::bn; double* th = scr + SC::th; double* dmv = scr + SC::dm;
+
+    const long long warps_total = (long long)gridDim.x * kJacWarps;
+    for (long long rod = (long long)blockIdx.x * kJacWarps + warp; rod < batch; rod += warps_total) {
+        // ---- nodal data: lanes 0..15 the rotation of node `lane`, lanes 16..31 the statics of node `lane - 16` ------------
+        if (lane < 16) {
+            const int i = lane;
+            if (i < N) {
+                quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+                if (i < M) { const double* s = Q + rod * 4 * M + i; q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M]; }
+                else if (q0) { const double* s = q0 + rod * 4; q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3]; }
+                double Rl[9];
+                {
+                    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+                    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+                    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+                    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+                    Rl[0] = 1 - (tyy + tzz); Rl[1] = txy - twz;       Rl[2] = txz + twy;
+                    Rl[3] = txy + twz;       Rl[4] = 1 - (txx + tzz); Rl[5] = tyz - twx;
+                    Rl[6] = txz - twy;       Rl[7] = tyz + twx;       Rl[8] = 1 - (txx + tyy);
+                }
+#pragma unroll
+                for (int e = 0; e < 9; ++e) Rs[9 * i + e] = Rl[e];
+                double g0 = 1.0, g1 = 0.0, g2 = 0.0;
+                if (Gamma) { const double* gm = Gamma + rod * 3 * N + i; g0 = gm[0]; g1 = gm[N]; g2 = gm[2 * N]; }
+                bs[3 * i] = Rl[0] * g0 + Rl[1] * g1 + Rl[2] * g2;
+                bs[3 * i + 1] = Rl[3] * g0 + Rl[4] * g1 + Rl[5] * g2;
+                bs[3 * i + 2] = Rl[6] * g0 + Rl[7] * g1 + Rl[8] * g2;
+            }
+        } else {
+            const int i = lane - 16;
+            if (i < N) {
+                if (i == 0) { const double* s = M_tip + rod * 3; ms[0] = s[0]; ms[1] = s[1]; ms[2] = s[2]; }
+                else {
+                    const double* s = min_ + rod * 3 * M + (i - 1); ms[3 * i] = s[0]; ms[3 * i + 1] = s[M]; ms[3 * i + 2] = s[2 * M];
+                    const double* f = nin + rod * 3 * M + (i - 1); ns[3 * i] = f[0]; ns[3 * i + 1] = f[M]; ns[3 * i + 2] = f[2 * M];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < 16) bns[lane] = bs[3 * lane] * ns[3 * lane] + bs[3 * lane + 1] * ns[3 * lane + 1] + bs[3 * lane + 2] * ns[3 * lane + 2];
+
+        double acc[2][NT][2];
+        // ---- dtheta = S u,  u[node j][3 d + comp] = P_k(t_j) R_j[comp][c] ----------------------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const int j = 4 * kt + cp;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int d = colD[nt], c = d / NE, k = d - NE * c;
+                double bv = Ps[k * 16 + j] * Rs[9 * j + 3 * colComp[nt] + c];
+                if (!colOk[nt] || j >= M) bv = 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], aS[mt][kt], bv);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                *reinterpret_cast<double2*>(th + (8 * mt + rho) * LD + 8 * nt + 2 * cp) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        __syncwarp();
+        // ---- dm = S_T v,  v[row j = node j+1][3 d + comp] = dth_c (b.n) - b_c (dth.n) -----------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const int node = 4 * kt + cp + 1;      // 1..16; node 16 does not exist (its scratch row is zero)
+            const bool live = node <= M;
+            const int nd = live ? node : 0;
+            const double n0 = ns[3 * nd], n1 = ns[3 * nd + 1], n2 = ns[3 * nd + 2];
+            const double b0 = bs[3 * nd], b1 = bs[3 * nd + 1], b2 = bs[3 * nd + 2];
+            const double bdn = bns[nd];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double* a = th + nd * LD + 3 * colD[nt];
+                const double a0 = a[0], a1 = a[1], a2 = a[2];
+                const double adn = a0 * n0 + a1 * n1 + a2 * n2;
+                const int comp = colComp[nt];
+                const double ac = comp == 0 ? a0 : (comp == 1 ? a1 : a2);
+                const double bc = comp == 0 ? b0 : (comp == 1 ? b1 : b2);
+                double bv = ac * bdn - bc * adn;
+                if (!colOk[nt] || !live) bv = 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], aT[mt][kt], bv);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)   // reduced row 8 mt + rho is node 8 mt + rho + 1 (row 0 of dmv, the tip, stays zero)
+                *reinterpret_cast<double2*>(dmv + (8 * mt + rho + 1) * LD + 8 * nt + 2 * cp) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        __syncwarp();
+        // ---- projection: J[(c',k')][d] = sum_i (w_i P_k'(t_i)) drho_i[c'][d],
+        //      drho_i[c'][d] = H_c' P_k(t_i) [c' == c] - sum_r R_i[r][c'] (dm_i - dth_i x m_i)_r -------------------------------
+        double pj[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { pj[nt][0] = 0.0; pj[nt][1] = 0.0; }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const int i = 4 * kt + cp;
+            const bool live = i < N;
+            const int nd = live ? i : 0;
+            const double m0 = ms[3 * nd], m1 = ms[3 * nd + 1], m2 = ms[3 * nd + 2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int d = prjD[nt], cq = prjC[nt], c = d / NE, k = d - NE * c;
+                const double* a = th + nd * LD + 3 * d;
+                const double* g = dmv + nd * LD + 3 * d;
+                const double a0 = a[0], a1 = a[1], a2 = a[2];
+                const double w0 = g[0] - (a1 * m2 - a2 * m1);
+                const double w1 = g[1] - (a2 * m0 - a0 * m2);
+                const double w2 = g[2] - (a0 * m1 - a1 * m0);
+                const double* Rc = Rs + 9 * nd + cq;
+                const double hk = (cq == c) ? (cq == 0 ? h0 : (cq == 1 ? h1 : h2)) * Ps[k * 16 + nd] : 0.0;
+                double bv = hk - (Rc[0] * w0 + Rc[3] * w1 + Rc[6] * w2);
+                if (!colOk[nt] || !live) bv = 0.0;
+                dmma_m8n8k4(pj[nt][0], pj[nt][1], aP[kt], bv);
+            }
+        }
+        // C fragment: row rho = k', columns 8 nt + 2 cp (+1) = c' ND + d  ->  J[(c' NE + k')][d], row-major ND x ND per rod
+        if (rho < NE) {
+            double* Jr = J + rod * ND * ND;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * nt + 2 * cp + e;
+                    if (col < 3 * ND) {
+                        const int cq = col / ND, d = col - ND * cq;
+                        Jr[(cq * NE + rho) * ND + d] = pj[nt][e];
+                    }
+                }
+        }
+        __syncwarp();  // the scratch is rewritten by the next rod
+    }
+}
+
+}  // namespace sri
