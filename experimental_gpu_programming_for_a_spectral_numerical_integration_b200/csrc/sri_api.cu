@@ -29,6 +29,7 @@
 #include "sri_stage_tma.cuh"
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
+#include "sri_wrench_generic.cuh"
 #include "sri_wrench_solve.cuh"
 
 // <row tiles per warp, column tiles, warps> of the N <= 32 instantiation of the multi-warp DMMA kernel
@@ -81,6 +82,9 @@ struct sri_context {
     double* d_ptab = nullptr;    // Legendre polynomials at the nodes, P_k(2 x_i - 1), [8][N]
     double* d_jac = nullptr;     // S = Dn_NN^-1 and S_T = D_TT^-1, row-major [M][M] each (sri_shape_jacobian), built on first use
     double* d_dnn = nullptr;     // Dn_NN, column-major [M][M] (sri_assemble_A), built on first use
+    double* d_wrench_scratch = nullptr;  // 58 <= N <= 64: per-CTA operator of sri_integrate_wrench_local (L2-resident)
+    size_t wrench_scratch_cap = 0;
+    int wrench_gen_occ = 0;
     int jac_occ[9] = {};         // resident CTAs per SM of shape_jacobian_dmma_kernel<ne>
     int jac_impl = 0;            // 0: DMMA kernel for N <= 16 (default), 1: SRI_JACOBIAN_IMPL=scalar everywhere (A/B measurements)
     const int* skip = nullptr;   // Newton loop with the device-side convergence flag: kernels launched while this is set take
@@ -845,6 +849,7 @@ int sri_destroy(sri_handle h) {
     if (guard.enter(h) != SRI_OK) { delete h; return SRI_ERR_CUDA; }
     if (h->nccl_comm) sri_nccl_finalize(h);
     if (h->d_dnn) cudaFree(h->d_dnn);
+    if (h->d_wrench_scratch) cudaFree(h->d_wrench_scratch);
     if (h->d_gather) cudaFree(h->d_gather);
     if (h->pipe_event) cudaEventDestroy(h->pipe_event);
     if (h->newton.host_state) cudaFreeHost(h->newton.host_state);
@@ -1029,9 +1034,12 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
     SRI_TRY(st.in(fbar, (size_t)batch * 3 * N, &p.fbar));
     SRI_TRY(st.in(F_tip, (size_t)batch * 3, &p.F_tip));
     SRI_TRY(st.out(n, (size_t)batch * 3 * M, &p.n));
-    if (h->R == 0 && !p.fbar) {
-        const long long total = (long long)batch * 3 * M;
-        sri::stress_noload_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16), 256, 0, h->stream>>>(batch, M, h->d_ops16 + sri::OpsLayout16::gT, p.F_tip, p.n);
+    if (!p.fbar) {
+        // no distributed load: n_i = gT_i F_tip, a pure streaming write (64 bytes per thread and pass, streaming stores)
+        const long long total = (long long)batch * 3 * M, chunks = (total + 7) / 8;
+        const double* gT = h->d_ops16 + (h->R == 0 ? sri::OpsLayout16::gT : sri::OpsLayoutGeneric{h->R}.gT());
+        const bool aligned = (reinterpret_cast<uintptr_t>(p.n) & 15u) == 0;
+        sri::stress_noload_kernel<<<(unsigned)std::min<long long>((chunks + 255) / 256, (long long)h->sm_count * 8), 256, 0, h->stream>>>(total, M, gT, p.F_tip, p.n, aligned ? 1 : 0);
         g_launches.fetch_add(1);
         SRI_CUDA(cudaGetLastError());
     } else if (h->R == 0) {
@@ -1121,7 +1129,6 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
                                const double* M_tip, double* Lambda, int* info) {
     SRI_ENTER(h);
     if (batch < 0 || (batch > 0 && (!K || !Q || !F_tip || !M_tip || !Lambda))) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_wrench_local: bad arguments");
-    if (h->N > 16) return fail(SRI_ERR_UNSUPPORTED_N, "sri_integrate_wrench_local: N <= 16 (use sri_wrench_local on the global-frame stages for larger N)");
     if (batch == 0) return SRI_OK;
     const int N = h->N, M = h->M;
     Staging st(h);
@@ -1137,10 +1144,36 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &p.Lambda));
     SRI_TRY(st.out(info, (size_t)batch, &p.info));
-    SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_kernel, h->device, sri::kWrenchSmem));
-    const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
-    const long long cap = (long long)h->sm_count;  // one CTA of 8 warps per SM (24 KB of shared memory per rod)
-    sri::wrench_local_solve_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchWarps, sri::kWrenchSmem, h->stream>>>(p);
+    if (N > 16) {
+        // one rod per CTA, dense 3M x 3M operator in shared memory while it fits (N <= 55), else in an L2-resident scratch
+        const int n = 3 * M, ld = n | 1;
+        sri::WrenchGenLayout L{n, ld, N, true};
+        bool in_smem = (size_t)L.total() * sizeof(double) <= 227 * 1024;
+        if (!in_smem) L.in_smem = false;
+        const size_t smem = (size_t)L.total() * sizeof(double);
+        SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_generic_kernel, h->device, smem));
+        int occ = 0;
+        SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::wrench_local_solve_generic_kernel, sri::kWrenchGenThreads, smem));
+        if (occ < 1) return fail(SRI_ERR_CUDA, "sri_integrate_wrench_local: kernel does not fit on this device");
+        const long long capg = (long long)h->sm_count * occ;
+        const int grid = (int)(batch < capg ? batch : capg);
+        if (!in_smem) {
+            const size_t need = (size_t)grid * n * ld * sizeof(double);
+            if (h->wrench_scratch_cap < need) {
+                SRI_CUDA(cudaStreamSynchronize(h->stream));
+                if (h->d_wrench_scratch) SRI_CUDA(cudaFree(h->d_wrench_scratch));
+                h->d_wrench_scratch = nullptr; h->wrench_scratch_cap = 0;
+                SRI_CUDA(cudaMalloc(&h->d_wrench_scratch, (size_t)capg * n * ld * sizeof(double)));
+                h->wrench_scratch_cap = (size_t)capg * n * ld * sizeof(double);
+            }
+        }
+        sri::wrench_local_solve_generic_kernel<<<grid, sri::kWrenchGenThreads, smem, h->stream>>>(p, h->d_wrench_scratch, in_smem ? 1 : 0);
+    } else {
+        SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_kernel, h->device, sri::kWrenchSmem));
+        const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
+        const long long cap = (long long)h->sm_count;  // one CTA of 8 warps per SM (24 KB of shared memory per rod)
+        sri::wrench_local_solve_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchWarps, sri::kWrenchSmem, h->stream>>>(p);
+    }
     g_launches.fetch_add(1);
     SRI_CUDA(cudaGetLastError());
     SRI_TRY(st.finish());
@@ -1318,6 +1351,15 @@ int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag
 }
 
 static int solve_small_dev(sri_context* h, int64_t batch, int n, double* A, const double* b, double* x, int* info) {
+    if (n == 3 || n == 6 || n == 9) {  // ne <= 3: the whole system lives in the thread's registers
+        const unsigned blocks = (unsigned)((batch + 63) / 64);
+        if (n == 3) solve_small_reg_kernel<3><<<blocks, 64, 0, h->stream>>>(batch, A, b, x, info, h->skip);
+        else if (n == 6) solve_small_reg_kernel<6><<<blocks, 64, 0, h->stream>>>(batch, A, b, x, info, h->skip);
+        else solve_small_reg_kernel<9><<<blocks, 64, 0, h->stream>>>(batch, A, b, x, info, h->skip);
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+        return SRI_OK;
+    }
     const int T = n <= 13 ? 128 : (n <= 19 ? 64 : 32);
     const size_t smem = (size_t)(n * n + n) * (T + 1) * sizeof(double);
     SRI_TRY(ensure_dynamic_smem(solve_small_kernel, h->device, smem));

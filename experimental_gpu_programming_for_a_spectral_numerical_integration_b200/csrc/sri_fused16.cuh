@@ -179,7 +179,8 @@ __device__ __forceinline__ void gj_step_rolled(quat (&c)[15], quat& b, int k, in
     // (warp-uniform tests).
     const int prow = 15 - (int)(key & 15u);
     const bool is_pivot = (row == prow) && !used;
-    if ((key >> 4) == 0u && sing == 0) sing = k + 1;
+    // zero pivot, or a non-finite one (hi word of |c|^2 >= 0x7ff00000: Inf / NaN in the strain samples)
+    if (((key >> 4) == 0u || (key >> 4) >= 0x07ff0000u) && sing == 0) sing = k + 1;
 #if SRI_BCAST_SHFL
     const int src = ((threadIdx.x & 16) | prow);
 #define SRI_PIVOT_ROW(j) shfl_quat(c[j], src)

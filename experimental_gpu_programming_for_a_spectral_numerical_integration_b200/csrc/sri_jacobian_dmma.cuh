@@ -11,9 +11,10 @@
 // All 3 ne directions of a rod go through the two integration matrices at once: two [16 x 16] x [16 x 9 ne]
 // contractions and one [ne x 16] x [16 x 9 ne] projection = (2 x 2 + 1) x 4 x NT DMMA m8n8k4, NT = ceil(9 ne / 8)
 // (80 DMMAs per rod at ne = 3), where the scalar kernel it replaces (shape_jacobian_kernel, still used for N > 16) spent
-// 2 x 15 x 45 x 9 FMAs per rod in one-lane dot products.  Every B fragment is evaluated by the lane that owns it
-// directly from the warp's nodal scratch (rotation matrices, b, n, m, and the two intermediate fields dth, dm), so the
-// only shared-memory round trips are those two fields.
+// 2 x 15 x 45 x 9 FMAs per rod in one-lane dot products.  The pointwise work between the contractions (v, drho) is done
+// once per (node, direction) item -- 16 x 3 ne items dealt to the 32 lanes -- and staged through the two field arrays of the
+// warp's scratch, from which the lanes then read their B fragments with plain loads (evaluating every B fragment in the
+// lane that owns it cost 3 x the FP64 work and 1.7 x the shared-memory loads and measured 447 us per 10^5 rods).
 //
 // Fragment layout of mma.sync.m8n8k4.f64 (rho = lane / 4, cp = lane % 4): A[row rho][k cp], B[k cp][col rho],
 // C[row rho][cols 2 cp, 2 cp + 1].
@@ -25,13 +26,13 @@ namespace sri {
 
 constexpr int kJacWarps = 4;
 #ifndef SRI_JAC_MINBLOCKS
-#define SRI_JAC_MINBLOCKS 3  // 168 registers: 12 warps per SM
+#define SRI_JAC_MINBLOCKS 4  // 128 registers (24 bytes of spills), 16 warps per SM: measured 364 us per 10^5 rods
 #endif
 
 template <int NE>
 struct JacDmmaScratch {  // doubles per warp
     static constexpr int NT = (9 * NE + 7) / 8;       // column tiles of the 9 NE = 3 (components) x 3 NE (directions) columns
-    static constexpr int LD = 8 * NT + 2;             // row stride of the two field arrays (even: double2 stores)
+    static constexpr int LD = 8 * NT + 4;             // row stride of the two field arrays: = 4 or 12 mod 16, so the B-fragment loads (rows cp, columns rho) of a half-warp fall on 16 distinct banks
     static constexpr int R = 0;                       // [16][9]  rotation matrices by node, row-major
     static constexpr int b = R + 144;                 // [16][3]  R Gamma
     static constexpr int n = b + 48;                  // [16][3]  internal force by node (node 0 unused)
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
     if (skip && *skip) return;
     using SC = JacDmmaScratch<NE>;
     constexpr int NT = SC::NT, LD = SC::LD, ND = 3 * NE;  // ND directions, 3 ND columns
+    constexpr int ITEMS = (16 * ND + 31) / 32;             // (node, direction) items per lane in the pointwise passes
     extern __shared__ __align__(16) double jsm[];
     double* Ps = jsm;            // [8][16] Legendre table, zero beyond node N-1
     double* Pw = jsm + 128;      // [8][16] w_i P_k(t_i)
@@ -81,8 +83,8 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
     for (int kt = 0; kt < 4; ++kt) aP[kt] = rho < NE ? Pw[rho * 16 + 4 * kt + cp] : 0.0;
 
     // per column tile: what this lane's B column (8 nt + rho) means
-    //   contractions: column = 3 d + comp          projection: column = c' ND + d
-    int colD[NT], colComp[NT], prjC[NT], prjD[NT];
+    //   contractions: column = 3 d + comp          (projection: column = c' ND + d)
+    int colD[NT], colComp[NT];
     bool colOk[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -90,7 +92,6 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
         colOk[nt] = col < 3 * ND;
         const int cc = colOk[nt] ? col : 0;
         colD[nt] = cc / 3; colComp[nt] = cc - 3 * colD[nt];
-        prjC[nt] = cc / ND; prjD[nt] = cc - ND * prjC[nt];
     }
 
     double* Rs = scr + SC::R; double* bs = scr + SC::b; double* ns = scr + SC::n; double* ms = scr + SC::m;
@@ -160,65 +161,93 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
             for (int nt = 0; nt < NT; ++nt)
                 *reinterpret_cast<double2*>(th + (8 * mt + rho) * LD + 8 * nt + 2 * cp) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         __syncwarp();
-        // ---- dm = S_T v,  v[row j = node j+1][3 d + comp] = dth_c (b.n) - b_c (dth.n) -----------------------------------------
+        // ---- v = dth (b.n) - b (dth.n) at nodes 1..M, one (node, direction) item per lane and pass, staged in the rows of
+        //      `dmv` (row = node) that the contraction below then overwrites with dm ---------------------------------------------
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int it = lane + 32 * r;
+            const int jn = it / ND, d = it - ND * jn;      // node jn + 1
+            if (jn < 16) {
+                const int node = jn + 1;
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                if (node <= M) {
+                    const double* a = th + node * LD + 3 * d;
+                    const double a0 = a[0], a1 = a[1], a2 = a[2];
+                    const double n0 = ns[3 * node], n1 = ns[3 * node + 1], n2 = ns[3 * node + 2];
+                    const double bdn = bns[node];
+                    const double adn = a0 * n0 + a1 * n1 + a2 * n2;
+                    v0 = a0 * bdn - bs[3 * node] * adn;
+                    v1 = a1 * bdn - bs[3 * node + 1] * adn;
+                    v2 = a2 * bdn - bs[3 * node + 2] * adn;
+                }
+                double* vd = dmv + node * LD + 3 * d;
+                vd[0] = v0; vd[1] = v1; vd[2] = v2;
+            }
+        }
+        __syncwarp();
+        // ---- dm = S_T v ------------------------------------------------------------------------------------------------------
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
-            const int node = 4 * kt + cp + 1;      // 1..16; node 16 does not exist (its scratch row is zero)
-            const bool live = node <= M;
-            const int nd = live ? node : 0;
-            const double n0 = ns[3 * nd], n1 = ns[3 * nd + 1], n2 = ns[3 * nd + 2];
-            const double b0 = bs[3 * nd], b1 = bs[3 * nd + 1], b2 = bs[3 * nd + 2];
-            const double bdn = bns[nd];
+            const double* vrow = dmv + (4 * kt + cp + 1) * LD + rho;   // B[k = reduced row 4 kt + cp][column 8 nt + rho]
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const double* a = th + nd * LD + 3 * colD[nt];
-                const double a0 = a[0], a1 = a[1], a2 = a[2];
-                const double adn = a0 * n0 + a1 * n1 + a2 * n2;
-                const int comp = colComp[nt];
-                const double ac = comp == 0 ? a0 : (comp == 1 ? a1 : a2);
-                const double bc = comp == 0 ? b0 : (comp == 1 ? b1 : b2);
-                double bv = ac * bdn - bc * adn;
-                if (!colOk[nt] || !live) bv = 0.0;
+                const double bv = vrow[8 * nt];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], aT[mt][kt], bv);
             }
         }
+        __syncwarp();  // every lane has read its v before the rows are overwritten
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)   // reduced row 8 mt + rho is node 8 mt + rho + 1 (row 0 of dmv, the tip, stays zero)
                 *reinterpret_cast<double2*>(dmv + (8 * mt + rho + 1) * LD + 8 * nt + 2 * cp) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         __syncwarp();
-        // ---- projection: J[(c',k')][d] = sum_i (w_i P_k'(t_i)) drho_i[c'][d],
-        //      drho_i[c'][d] = H_c' P_k(t_i) [c' == c] - sum_r R_i[r][c'] (dm_i - dth_i x m_i)_r -------------------------------
+        // ---- drho_i[c'][d] = H_c' P_k(t_i) [c' == c] - sum_r R_i[r][c'] (dm_i - dth_i x m_i)_r, one (node, direction) item per
+        //      lane and pass; kept in registers until every lane has read dth, then staged in `th` with column c' ND + d ----------
+        double dr[ITEMS][3];
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int it = lane + 32 * r;
+            const int i = it / ND, d = it - ND * i;
+            dr[r][0] = 0.0; dr[r][1] = 0.0; dr[r][2] = 0.0;
+            if (i < N) {
+                const int c = d / NE, k = d - NE * c;
+                const double* a = th + i * LD + 3 * d;
+                const double* g = dmv + i * LD + 3 * d;
+                const double a0 = a[0], a1 = a[1], a2 = a[2];
+                const double m0 = ms[3 * i], m1 = ms[3 * i + 1], m2 = ms[3 * i + 2];
+                const double w0 = g[0] - (a1 * m2 - a2 * m1);
+                const double w1 = g[1] - (a2 * m0 - a0 * m2);
+                const double w2 = g[2] - (a0 * m1 - a1 * m0);
+                const double* Ri = Rs + 9 * i;
+                const double hk = (c == 0 ? h0 : (c == 1 ? h1 : h2)) * Ps[k * 16 + i];
+                dr[r][0] = (c == 0 ? hk : 0.0) - (Ri[0] * w0 + Ri[3] * w1 + Ri[6] * w2);
+                dr[r][1] = (c == 1 ? hk : 0.0) - (Ri[1] * w0 + Ri[4] * w1 + Ri[7] * w2);
+                dr[r][2] = (c == 2 ? hk : 0.0) - (Ri[2] * w0 + Ri[5] * w1 + Ri[8] * w2);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int it = lane + 32 * r;
+            const int i = it / ND, d = it - ND * i;
+            if (i < 16) { double* o = th + i * LD + d; o[0] = dr[r][0]; o[ND] = dr[r][1]; o[2 * ND] = dr[r][2]; }
+        }
+        __syncwarp();
+        // ---- projection: J[(c',k')][d] = sum_i (w_i P_k'(t_i)) drho_i[c'][d] -------------------------------------------------------
         double pj[NT][2];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { pj[nt][0] = 0.0; pj[nt][1] = 0.0; }
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
-            const int i = 4 * kt + cp;
-            const bool live = i < N;
-            const int nd = live ? i : 0;
-            const double m0 = ms[3 * nd], m1 = ms[3 * nd + 1], m2 = ms[3 * nd + 2];
+            const double* drow = th + (4 * kt + cp) * LD + rho;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int d = prjD[nt], cq = prjC[nt], c = d / NE, k = d - NE * c;
-                const double* a = th + nd * LD + 3 * d;
-                const double* g = dmv + nd * LD + 3 * d;
-                const double a0 = a[0], a1 = a[1], a2 = a[2];
-                const double w0 = g[0] - (a1 * m2 - a2 * m1);
-                const double w1 = g[1] - (a2 * m0 - a0 * m2);
-                const double w2 = g[2] - (a0 * m1 - a1 * m0);
-                const double* Rc = Rs + 9 * nd + cq;
-                const double hk = (cq == c) ? (cq == 0 ? h0 : (cq == 1 ? h1 : h2)) * Ps[k * 16 + nd] : 0.0;
-                double bv = hk - (Rc[0] * w0 + Rc[3] * w1 + Rc[6] * w2);
-                if (!colOk[nt] || !live) bv = 0.0;
-                dmma_m8n8k4(pj[nt][0], pj[nt][1], aP[kt], bv);
-            }
+            for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(pj[nt][0], pj[nt][1], aP[kt], drow[8 * nt]);
         }
         // C fragment: row rho = k', columns 8 nt + 2 cp (+1) = c' ND + d  ->  J[(c' NE + k')][d], row-major ND x ND per rod
         if (rho < NE) {

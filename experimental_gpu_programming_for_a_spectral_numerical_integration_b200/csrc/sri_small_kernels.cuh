@@ -527,6 +527,66 @@ __global__ void solve_small_kernel(long long batch, int n, const double* __restr
     for (int e = tid; e < count * n; e += T) { const int sys = e / n, el = e - sys * n; xs[e] = ssm[(nn + el) * LD + sys]; }
 }
 
+// The same solve for the small orders of the shape problem (n = 3 ne, ne <= 3) with the whole system in registers: every
+// index is a compile-time constant, the row exchange of the partial pivoting is a chain of predicated swaps, and the
+// thread reads its own contiguous 8 n (n + 1) bytes straight from global memory (a warp's systems are one contiguous
+// region, so every fetched sector is consumed).  Same arithmetic as solve_small_kernel: identical results.
+template <int NN>
+__global__ void __launch_bounds__(64) solve_small_reg_kernel(long long batch, const double* __restrict__ A, const double* __restrict__ b,
+                                                             double* __restrict__ x, int* __restrict__ info, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= batch) return;
+    double a[NN][NN], r[NN];
+    {
+        const double* src = A + s * NN * NN;
+#pragma unroll
+        for (int i = 0; i < NN; ++i)
+#pragma unroll
+            for (int j = 0; j < NN; ++j) a[i][j] = src[i * NN + j];
+        const double* bs = b + s * NN;
+#pragma unroll
+        for (int e = 0; e < NN; ++e) r[e] = bs[e];
+    }
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+        int p = k;
+        double best = fabs(a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < NN; ++i) { const double v = fabs(a[i][k]); if (v > best) { best = v; p = i; } }
+        const bool ok = best != 0.0;   // a zero column is skipped (multipliers 0), as in solve_small_kernel
+        if (!ok && !bad) bad = k + 1;
+#pragma unroll
+        for (int i = k + 1; i < NN; ++i) {  // row exchange k <-> p by selects: no branch, every index static
+            const bool sw = ok && (p == i);
+#pragma unroll
+            for (int j = k; j < NN; ++j) { const double t = a[k][j]; a[k][j] = sw ? a[i][j] : t; a[i][j] = sw ? t : a[i][j]; }
+            const double t = r[k]; r[k] = sw ? r[i] : t; r[i] = sw ? t : r[i];
+        }
+        const double inv = ok ? 1.0 / a[k][k] : 0.0;
+        const double rk = r[k];
+#pragma unroll
+        for (int i = k + 1; i < NN; ++i) {
+            const double l = a[i][k] * inv;
+#pragma unroll
+            for (int j = k + 1; j < NN; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
+            r[i] = fma(-l, rk, r[i]);
+        }
+    }
+#pragma unroll
+    for (int k = NN - 1; k >= 0; --k) {
+        double v = r[k];
+#pragma unroll
+        for (int j = k + 1; j < NN; ++j) v = fma(-a[k][j], r[j], v);
+        r[k] = v / a[k][k];
+    }
+    if (info) info[s] = bad;
+    double* xs = x + s * NN;
+#pragma unroll
+    for (int e = 0; e < NN; ++e) xs[e] = r[e];
+}
+
 // SURVEY 8(d) synthetic rods.  One thread per rod.
 __global__ void generate_rods_kernel(unsigned long long seed, long long first_rod, long long batch, int N,
                                      const double* __restrict__ tnodes, double* __restrict__ K,

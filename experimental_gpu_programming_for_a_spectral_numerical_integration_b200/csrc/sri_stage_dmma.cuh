@@ -144,14 +144,39 @@ __global__ void SRI_STAGE_BOUNDS stage_dmma_kernel(const FusedParams p) {
     }
 }
 
-// n_i = gT_i F_tip when there is no distributed load: pure streaming, no contraction needed.
-__global__ void stress_noload_kernel(long long batch, int M, const double* __restrict__ gT, const double* __restrict__ F_tip,
-                                     double* __restrict__ n) {
-    const long long total = batch * 3 * M;
+// n_i = gT_i F_tip when there is no distributed load: pure streaming write, no contraction needed (any N <= 64).
+// A thread produces 8 consecutive doubles of the [batch][3][M] output per pass: one division locates its (rod, component)
+// row, then it walks along the rows; a warp's stores cover 2 KB of contiguous memory as 128-bit streaming stores.
+__global__ void __launch_bounds__(256) stress_noload_kernel(long long total, int M, const double* __restrict__ gT,
+                                                            const double* __restrict__ F_tip, double* __restrict__ n, int aligned16) {
+    __shared__ double g[64];
+    if (threadIdx.x < M) g[threadIdx.x] = gT[threadIdx.x];
+    __syncthreads();
+    const long long chunks = (total + 7) >> 3;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int i = (int)(idx % M);
-        n[idx] = gT[i] * __ldg(F_tip + idx / M);
+    const bool small = total <= 0x7fffffffLL;  // 32-bit index arithmetic covers 2^31 output doubles
+    for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < chunks; ch += stride) {
+        const long long idx0 = ch << 3;
+        long long u;
+        int i;
+        if (small) { const unsigned q = (unsigned)idx0 / (unsigned)M; u = q; i = (int)((unsigned)idx0 - q * (unsigned)M); }
+        else { u = idx0 / M; i = (int)(idx0 - u * M); }
+        const long long left = total - idx0;  // >= 1
+        double f = __ldg(F_tip + u);
+        double v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            v[e] = g[i] * f;
+            if (++i == M) { i = 0; ++u; if (e + 1 < left && e < 7) f = __ldg(F_tip + u); }
+        }
+        double* d = n + idx0;
+        if (left >= 8 && aligned16) {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) __stcs(reinterpret_cast<double2*>(d + e), make_double2(v[e], v[e + 1]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (e < left) d[e] = v[e];
+        }
     }
 }
 

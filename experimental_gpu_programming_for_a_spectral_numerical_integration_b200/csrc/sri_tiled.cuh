@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(32 * H, (LPR == 16 ? 3 : 1)) tiled_kernel(cons
                 if (ln == 0) {
                     pinfo[par * RPW + sub] = prow;
                     perm[sub * 64 + kk] = prow;
-                    if ((key >> 6) == 0u && sing[sub] == 0) sing[sub] = kk + 1;
+                    if (((key >> 6) == 0u || (key >> 6) >= 0x01ffc000u) && sing[sub] == 0) sing[sub] = kk + 1;  // zero or non-finite pivot
                 }
             };
 #if SRI_TILED_LOOKAHEAD

@@ -91,7 +91,7 @@ int sri_assemble_A(sri_handle h, int64_t batch, const double* K, double* A_NN);
 /* integrateQuaternions()  main.cpp:91-118 with updateA main.cpp:55-88.
  * Solves ((I4 (x) Dn_NN) - 1/2 blockdiag A(K_i)) Q = -D_IN q0 per rod.
  * K [batch][3][N]; q0 [batch][4] (w,x,y,z) or NULL => (1,0,0,0) (main.cpp:106-107); Q [batch][4][M];
- * info [batch] or NULL: 0 ok, k>0 = zero pivot met at elimination step k (the reference would return inf/NaN). */
+ * info [batch] or NULL: 0 ok, k>0 = zero or non-finite pivot met at elimination step k (the reference would return inf/NaN). */
 int sri_integrate_quaternions(sri_handle h, int64_t batch, const double* K, const double* q0, double* Q,
                               int* info);
 
@@ -176,7 +176,8 @@ int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double*
  *   N' = -K^ N - R^T fbar,  C' = -K^ C - Gamma^ N - R^T lbar,  N(1) = R(1)^T F_tip,  C(1) = R(1)^T M_tip,
  * collocated with the tip node eliminated: the strain-dependent operator D_TT (x) I3 + blockdiag(K^_i) (3M x 3M), one
  * partial-pivot LU per rod and two solves.  Agrees with sri_wrench_local on the global-frame stages to the
- * discretisation error (1e-8 at N = 16).  N <= 16.  K [batch][3][N]; Q [batch][4][M] from stage 1; optional inputs as
+ * discretisation error (1e-8 at N = 16, round-off from N = 32).  One rod per warp for N <= 16 (blocked LU, trailing update
+ * on the tensor cores), one rod per CTA for 17 <= N <= 64.  K [batch][3][N]; Q [batch][4][M] from stage 1; optional inputs as
  * in sri_integrate_all; Lambda [batch][6][N], couple first; info [batch] or NULL (zero-pivot step of the LU). */
 int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, const double* Q, const double* q0,
                                const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
