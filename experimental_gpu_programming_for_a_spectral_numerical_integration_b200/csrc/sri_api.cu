@@ -1035,8 +1035,8 @@ int sri_integrate_stress(sri_handle h, int64_t batch, const double* fbar, const 
     SRI_TRY(st.in(F_tip, (size_t)batch * 3, &p.F_tip));
     SRI_TRY(st.out(n, (size_t)batch * 3 * M, &p.n));
     if (!p.fbar) {
-        // no distributed load: n_i = gT_i F_tip, a pure streaming write (64 bytes per thread and pass, streaming stores)
-        const long long total = (long long)batch * 3 * M, chunks = (total + 7) / 8;
+        // no distributed load: n_i = gT_i F_tip, a pure streaming write (one 2 KB tile per warp and pass, 128-bit streaming stores)
+        const long long total = (long long)batch * 3 * M, chunks = (total + 255) / 256 * 32;  // 32 lanes per 2 KB tile
         const double* gT = h->d_ops16 + (h->R == 0 ? sri::OpsLayout16::gT : sri::OpsLayoutGeneric{h->R}.gT());
         const bool aligned = (reinterpret_cast<uintptr_t>(p.n) & 15u) == 0;
         sri::stress_noload_kernel<<<(unsigned)std::min<long long>((chunks + 255) / 256, (long long)h->sm_count * 8), 256, 0, h->stream>>>(total, M, gT, p.F_tip, p.n, aligned ? 1 : 0);

@@ -20,19 +20,21 @@
 // C[row rho][cols 2 cp, 2 cp + 1].
 #pragma once
 #include "sri_device.cuh"
+#include "sri_fused16.cuh"     // cp_async8
 #include "sri_stage_dmma.cuh"  // dmma_m8n8k4, StageTables
 
 namespace sri {
 
 constexpr int kJacWarps = 4;
 #ifndef SRI_JAC_MINBLOCKS
-#define SRI_JAC_MINBLOCKS 4  // 128 registers (24 bytes of spills), 16 warps per SM: measured 364 us per 10^5 rods
+#define SRI_JAC_MINBLOCKS 2  // measured per 10^5 rods: 2 CTAs per SM (255 registers, no spills) 245 us, 3 (168 registers) 289 us, 4 (128) 315 us
 #endif
 
 template <int NE>
 struct JacDmmaScratch {  // doubles per warp
     static constexpr int NT = (9 * NE + 7) / 8;       // column tiles of the 9 NE = 3 (components) x 3 NE (directions) columns
-    static constexpr int LD = 8 * NT + 4;             // row stride of the two field arrays: = 4 or 12 mod 16, so the B-fragment loads (rows cp, columns rho) of a half-warp fall on 16 distinct banks
+    static constexpr int LD = 8 * NT + 2;             // row stride of the two field arrays: = 2 mod 16 when NT is even, which keeps the
+                                                      // pointwise passes (lane = (node, direction parity)) free of bank conflicts
     static constexpr int R = 0;                       // [16][9]  rotation matrices by node, row-major
     static constexpr int b = R + 144;                 // [16][3]  R Gamma
     static constexpr int n = b + 48;                  // [16][3]  internal force by node (node 0 unused)
@@ -40,7 +42,8 @@ struct JacDmmaScratch {  // doubles per warp
     static constexpr int bn = m + 48;                 // [16]     b . n
     static constexpr int th = bn + 16;                // [16][LD] dtheta by node, column 3 d + comp
     static constexpr int dm = th + 16 * LD;           // [17][LD] dm by node (row 0 = tip = 0, row 16 = padding)
-    static constexpr int total = dm + 17 * LD;
+    static constexpr int pre = dm + 17 * LD;          // [2][7][32] raw nodal inputs of this and the next rod (cp.async staging)
+    static constexpr int total = pre + 2 * 7 * 32;
 };
 
 template <int NE>
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
     if (skip && *skip) return;
     using SC = JacDmmaScratch<NE>;
     constexpr int NT = SC::NT, LD = SC::LD, ND = 3 * NE;  // ND directions, 3 ND columns
-    constexpr int ITEMS = (16 * ND + 31) / 32;             // (node, direction) items per lane in the pointwise passes
+    constexpr int ITEMS = (ND + 1) / 2;                    // pointwise passes: lane = (node, parity), directions d = parity + 2 r
     extern __shared__ __align__(16) double jsm[];
     double* Ps = jsm;            // [8][16] Legendre table, zero beyond node N-1
     double* Pw = jsm + 128;      // [8][16] w_i P_k(t_i)
@@ -94,32 +97,81 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
         colD[nt] = cc / 3; colComp[nt] = cc - 3 * colD[nt];
     }
 
+    // rod-independent factors in registers: P_k(t_j) of this lane's B entries in the first contraction (0 where the entry is
+    // structurally zero), and P_k(t_node) of the node this lane serves in the pointwise passes
+    double pk1[4][NT];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int j = 4 * kt + cp, d = colD[nt], k = d - NE * (d / NE);
+            pk1[kt][nt] = (colOk[nt] && j < M) ? Ps[k * 16 + j] : 0.0;
+        }
+    const int pnode = lane >> 1, dpar = lane & 1;
+    double pkn[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) pkn[k] = Ps[k * 16 + pnode];
+
     double* Rs = scr + SC::R; double* bs = scr + SC::b; double* ns = scr + SC::n; double* ms = scr + SC::m;
-    double* bns = scr + SC::bn; double* th = scr + SC::th; double* dmv = scr + SC::dm;
+    double* th = scr + SC::th; double* dmv = scr + SC::dm;
 
     const long long warps_total = (long long)gridDim.x * kJacWarps;
-    for (long long rod = (long long)blockIdx.x * kJacWarps + warp; rod < batch; rod += warps_total) {
-        // ---- nodal data: lanes 0..15 the rotation of node `lane`, lanes 16..31 the statics of node `lane - 16` ------------
+    // This lane's raw nodal inputs of one rod -- lanes 0..15 the quaternion (and Gamma) of node `lane`, lanes 16..31 the couple
+    // and force of node `lane - 16` -- are copied one rod ahead into the staging slots with cp.async, so that the global-memory
+    // latency hides behind the previous rod without holding registers.  Slot layout [7][32]: entry e of lane l at e * 32 + l.
+    auto prefetch = [&](long long rod_, int slot) {
+        double* st = scr + SC::pre + slot * 224 + lane;
+        if (lane < 16) {
+            const int i = lane;
+            if (i < M) { const double* q = Q + rod_ * 4 * M + i; cp_async8(st, q); cp_async8(st + 32, q + M); cp_async8(st + 64, q + 2 * M); cp_async8(st + 96, q + 3 * M); }
+            else if (i == M && q0) { const double* q = q0 + rod_ * 4; cp_async8(st, q); cp_async8(st + 32, q + 1); cp_async8(st + 64, q + 2); cp_async8(st + 96, q + 3); }
+            if (Gamma && i < N) { const double* gm = Gamma + rod_ * 3 * N + i; cp_async8(st + 128, gm); cp_async8(st + 160, gm + N); cp_async8(st + 192, gm + 2 * N); }
+        } else {
+            const int i = lane - 16;
+            if (i == 0) { const double* t = M_tip + rod_ * 3; cp_async8(st, t); cp_async8(st + 32, t + 1); cp_async8(st + 64, t + 2); }
+            else if (i < N) {
+                const double* t = min_ + rod_ * 3 * M + (i - 1); cp_async8(st, t); cp_async8(st + 32, t + M); cp_async8(st + 64, t + 2 * M);
+                const double* f = nin + rod_ * 3 * M + (i - 1); cp_async8(st + 96, f); cp_async8(st + 128, f + M); cp_async8(st + 160, f + 2 * M);
+            }
+        }
+    };
+    const long long rod_first = (long long)blockIdx.x * kJacWarps + warp;
+    if (rod_first < batch) prefetch(rod_first, 0);
+    cp_async_commit();
+    int it = 0;
+    for (long long rod = rod_first; rod < batch; rod += warps_total, ++it) {
+        if (rod + warps_total < batch) prefetch(rod + warps_total, (it + 1) & 1);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed: this rod's inputs have landed
+        __syncwarp();
+        double cur[7];
+        {
+            const double* st = scr + SC::pre + (it & 1) * 224 + lane;
+#pragma unroll
+            for (int e = 0; e < 7; ++e) cur[e] = st[32 * e];
+            if (lane < 16) {
+                if (!(lane < M || (lane == M && q0))) { cur[0] = 1.0; cur[1] = 0.0; cur[2] = 0.0; cur[3] = 0.0; }  // identity (base node without q0)
+                if (!Gamma) { cur[4] = 1.0; cur[5] = 0.0; cur[6] = 0.0; }
+            }
+        }
+        // ---- nodal data -> the warp's scratch ---------------------------------------------------------------------------------
         if (lane < 16) {
             const int i = lane;
             if (i < N) {
-                quat q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
-                if (i < M) { const double* s = Q + rod * 4 * M + i; q.w = s[0]; q.x = s[M]; q.y = s[2 * M]; q.z = s[3 * M]; }
-                else if (q0) { const double* s = q0 + rod * 4; q.w = s[0]; q.x = s[1]; q.y = s[2]; q.z = s[3]; }
                 double Rl[9];
                 {
-                    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
-                    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
-                    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
-                    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+                    const double qw = cur[0], qx = cur[1], qy = cur[2], qz = cur[3];
+                    const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+                    const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+                    const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+                    const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
                     Rl[0] = 1 - (tyy + tzz); Rl[1] = txy - twz;       Rl[2] = txz + twy;
                     Rl[3] = txy + twz;       Rl[4] = 1 - (txx + tzz); Rl[5] = tyz - twx;
                     Rl[6] = txz - twy;       Rl[7] = tyz + twx;       Rl[8] = 1 - (txx + tyy);
                 }
 #pragma unroll
                 for (int e = 0; e < 9; ++e) Rs[9 * i + e] = Rl[e];
-                double g0 = 1.0, g1 = 0.0, g2 = 0.0;
-                if (Gamma) { const double* gm = Gamma + rod * 3 * N + i; g0 = gm[0]; g1 = gm[N]; g2 = gm[2 * N]; }
+                const double g0 = cur[4], g1 = cur[5], g2 = cur[6];
                 bs[3 * i] = Rl[0] * g0 + Rl[1] * g1 + Rl[2] * g2;
                 bs[3 * i + 1] = Rl[3] * g0 + Rl[4] * g1 + Rl[5] * g2;
                 bs[3 * i + 2] = Rl[6] * g0 + Rl[7] * g1 + Rl[8] * g2;
@@ -127,15 +179,13 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
         } else {
             const int i = lane - 16;
             if (i < N) {
-                if (i == 0) { const double* s = M_tip + rod * 3; ms[0] = s[0]; ms[1] = s[1]; ms[2] = s[2]; }
-                else {
-                    const double* s = min_ + rod * 3 * M + (i - 1); ms[3 * i] = s[0]; ms[3 * i + 1] = s[M]; ms[3 * i + 2] = s[2 * M];
-                    const double* f = nin + rod * 3 * M + (i - 1); ns[3 * i] = f[0]; ns[3 * i + 1] = f[M]; ns[3 * i + 2] = f[2 * M];
-                }
+                ms[3 * i] = cur[0]; ms[3 * i + 1] = cur[1]; ms[3 * i + 2] = cur[2];
+                if (i >= 1) { ns[3 * i] = cur[3]; ns[3 * i + 1] = cur[4]; ns[3 * i + 2] = cur[5]; }
             }
         }
         __syncwarp();
-        if (lane < 16) bns[lane] = bs[3 * lane] * ns[3 * lane] + bs[3 * lane + 1] * ns[3 * lane + 1] + bs[3 * lane + 2] * ns[3 * lane + 2];
+
+        __syncwarp();
 
         double acc[2][NT][2];
         // ---- dtheta = S u,  u[node j][3 d + comp] = P_k(t_j) R_j[comp][c] ----------------------------------------------------
@@ -148,9 +198,7 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
             const int j = 4 * kt + cp;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const int d = colD[nt], c = d / NE, k = d - NE * c;
-                double bv = Ps[k * 16 + j] * Rs[9 * j + 3 * colComp[nt] + c];
-                if (!colOk[nt] || j >= M) bv = 0.0;
+                const double bv = pk1[kt][nt] * Rs[9 * j + 3 * colComp[nt] + colD[nt] / NE];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], aS[mt][kt], bv);
             }
@@ -161,27 +209,24 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
             for (int nt = 0; nt < NT; ++nt)
                 *reinterpret_cast<double2*>(th + (8 * mt + rho) * LD + 8 * nt + 2 * cp) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         __syncwarp();
-        // ---- v = dth (b.n) - b (dth.n) at nodes 1..M, one (node, direction) item per lane and pass, staged in the rows of
-        //      `dmv` (row = node) that the contraction below then overwrites with dm ---------------------------------------------
+        // ---- v = dth (b.n) - b (dth.n) at nodes 1..M: lane (node, parity) loads its node's b and n once and walks over its
+        //      directions; staged in the rows of `dmv` (row = node) that the contraction below then overwrites with dm ------------
+        if (pnode >= 1 && pnode <= M) {
+            const double n0 = ns[3 * pnode], n1 = ns[3 * pnode + 1], n2 = ns[3 * pnode + 2];
+            const double b0 = bs[3 * pnode], b1 = bs[3 * pnode + 1], b2 = bs[3 * pnode + 2];
+            const double bdn = b0 * n0 + b1 * n1 + b2 * n2;
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-            const int it = lane + 32 * r;
-            const int jn = it / ND, d = it - ND * jn;      // node jn + 1
-            if (jn < 16) {
-                const int node = jn + 1;
-                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-                if (node <= M) {
-                    const double* a = th + node * LD + 3 * d;
+            for (int r = 0; r < ITEMS; ++r) {
+                const int d = dpar + 2 * r;
+                if (d < ND) {
+                    const double* a = th + pnode * LD + 3 * d;
                     const double a0 = a[0], a1 = a[1], a2 = a[2];
-                    const double n0 = ns[3 * node], n1 = ns[3 * node + 1], n2 = ns[3 * node + 2];
-                    const double bdn = bns[node];
                     const double adn = a0 * n0 + a1 * n1 + a2 * n2;
-                    v0 = a0 * bdn - bs[3 * node] * adn;
-                    v1 = a1 * bdn - bs[3 * node + 1] * adn;
-                    v2 = a2 * bdn - bs[3 * node + 2] * adn;
+                    double* vd = dmv + pnode * LD + 3 * d;
+                    vd[0] = a0 * bdn - b0 * adn;
+                    vd[1] = a1 * bdn - b1 * adn;
+                    vd[2] = a2 * bdn - b2 * adn;
                 }
-                double* vd = dmv + node * LD + 3 * d;
-                vd[0] = v0; vd[1] = v1; vd[2] = v2;
             }
         }
         __syncwarp();
@@ -207,36 +252,43 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
             for (int nt = 0; nt < NT; ++nt)   // reduced row 8 mt + rho is node 8 mt + rho + 1 (row 0 of dmv, the tip, stays zero)
                 *reinterpret_cast<double2*>(dmv + (8 * mt + rho + 1) * LD + 8 * nt + 2 * cp) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         __syncwarp();
-        // ---- drho_i[c'][d] = H_c' P_k(t_i) [c' == c] - sum_r R_i[r][c'] (dm_i - dth_i x m_i)_r, one (node, direction) item per
-        //      lane and pass; kept in registers until every lane has read dth, then staged in `th` with column c' ND + d ----------
+        // ---- drho_i[c'][d] = H_c' P_k(t_i) [c' == c] - sum_r R_i[r][c'] (dm_i - dth_i x m_i)_r: lane (node, parity) loads its node's
+        //      m and R once; results stay in registers until every lane has read dth, then go to `th` with column c' ND + d -------
         double dr[ITEMS][3];
+        {
+            const bool live = pnode < N;
+            const int nd = live ? pnode : 0;
+            const double m0 = ms[3 * nd], m1 = ms[3 * nd + 1], m2 = ms[3 * nd + 2];
+            double Rl[9];
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-            const int it = lane + 32 * r;
-            const int i = it / ND, d = it - ND * i;
-            dr[r][0] = 0.0; dr[r][1] = 0.0; dr[r][2] = 0.0;
-            if (i < N) {
-                const int c = d / NE, k = d - NE * c;
-                const double* a = th + i * LD + 3 * d;
-                const double* g = dmv + i * LD + 3 * d;
-                const double a0 = a[0], a1 = a[1], a2 = a[2];
-                const double m0 = ms[3 * i], m1 = ms[3 * i + 1], m2 = ms[3 * i + 2];
-                const double w0 = g[0] - (a1 * m2 - a2 * m1);
-                const double w1 = g[1] - (a2 * m0 - a0 * m2);
-                const double w2 = g[2] - (a0 * m1 - a1 * m0);
-                const double* Ri = Rs + 9 * i;
-                const double hk = (c == 0 ? h0 : (c == 1 ? h1 : h2)) * Ps[k * 16 + i];
-                dr[r][0] = (c == 0 ? hk : 0.0) - (Ri[0] * w0 + Ri[3] * w1 + Ri[6] * w2);
-                dr[r][1] = (c == 1 ? hk : 0.0) - (Ri[1] * w0 + Ri[4] * w1 + Ri[7] * w2);
-                dr[r][2] = (c == 2 ? hk : 0.0) - (Ri[2] * w0 + Ri[5] * w1 + Ri[8] * w2);
+            for (int e = 0; e < 9; ++e) Rl[e] = Rs[9 * nd + e];
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                const int d = dpar + 2 * r;
+                dr[r][0] = 0.0; dr[r][1] = 0.0; dr[r][2] = 0.0;
+                if (d < ND && live) {
+                    const int c = d / NE, k = d - NE * c;
+                    const double* a = th + nd * LD + 3 * d;
+                    const double* g = dmv + nd * LD + 3 * d;
+                    const double a0 = a[0], a1 = a[1], a2 = a[2];
+                    const double w0 = g[0] - (a1 * m2 - a2 * m1);
+                    const double w1 = g[1] - (a2 * m0 - a0 * m2);
+                    const double w2 = g[2] - (a0 * m1 - a1 * m0);
+                    double pv = pkn[0];
+#pragma unroll
+                    for (int kk = 1; kk < NE; ++kk) pv = (k == kk) ? pkn[kk] : pv;
+                    const double hk = (c == 0 ? h0 : (c == 1 ? h1 : h2)) * pv;
+                    dr[r][0] = (c == 0 ? hk : 0.0) - (Rl[0] * w0 + Rl[3] * w1 + Rl[6] * w2);
+                    dr[r][1] = (c == 1 ? hk : 0.0) - (Rl[1] * w0 + Rl[4] * w1 + Rl[7] * w2);
+                    dr[r][2] = (c == 2 ? hk : 0.0) - (Rl[2] * w0 + Rl[5] * w1 + Rl[8] * w2);
+                }
             }
         }
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
-            const int it = lane + 32 * r;
-            const int i = it / ND, d = it - ND * i;
-            if (i < 16) { double* o = th + i * LD + d; o[0] = dr[r][0]; o[ND] = dr[r][1]; o[2 * ND] = dr[r][2]; }
+            const int d = dpar + 2 * r;
+            if (d < ND) { double* o = th + pnode * LD + d; o[0] = dr[r][0]; o[ND] = dr[r][1]; o[2 * ND] = dr[r][2]; }
         }
         __syncwarp();
         // ---- projection: J[(c',k')][d] = sum_i (w_i P_k'(t_i)) drho_i[c'][d] -------------------------------------------------------
@@ -265,6 +317,7 @@ __global__ void __launch_bounds__(32 * kJacWarps, NE <= 4 ? SRI_JAC_MINBLOCKS : 
         }
         __syncwarp();  // the scratch is rewritten by the next rod
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace sri

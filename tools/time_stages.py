@@ -30,3 +30,9 @@ for name, (fn, bytes_per_rod) in cases.items():
     ms = timeit(fn)
     print(json.dumps({"stage": name, "N": N, "rods": B, "ms": round(ms, 4), "rods_per_s": B / ms * 1e3, "GBps": B * bytes_per_rod / ms * 1e-6,
                       "frac_of_hbm_6546": B * bytes_per_rod / ms * 1e-6 / 6546.2}))
+
+# calibration of the pure-write roof: a device memset of the same number of bytes as the no-load force stage writes
+buf = torch.empty((B * 3 * M,), dtype=f64, device='cuda')
+ms = timeit(lambda: buf.zero_())
+print(json.dumps({"stage": "memset_same_bytes (cudaMemset-class fill, write-only roof)", "N": N, "rods": B, "ms": round(ms, 4),
+                  "GBps": B * 3 * M * 8 / ms * 1e-6, "frac_of_hbm_6546": B * 3 * M * 8 / ms * 1e-6 / 6546.2}))
