@@ -99,6 +99,26 @@ def _host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def _reference_own_code_rate():
+    """Side figure: the reference's OWN main.cpp functions (integrateQuaternions() + integratePosition(), compiled verbatim in the
+    build container against oracle/eigen_shim, oracle/_ref/libreference_harness.so) on one host core -- stages 1-2 only, the
+    second quaternion solve of main.cpp:147 included, global qe => not thread-safe.  None when the prebuilt library is absent."""
+    try:
+        from oracle.build_reference import ReferenceHarness
+        from oracle.oracle import Oracle
+        h = ReferenceHarness()
+        qe = Oracle(N_NODES).generate_modes(SEED, 0, 600)
+        h.integrate(qe[:50])
+        t0 = time.perf_counter()
+        h.integrate(qe)
+        dt = time.perf_counter() - t0
+        return {"value": len(qe) / dt, "unit": "rods/s", "cores": 1, "kind": "reference",
+                "sample": "600 rods, main.cpp's own integrateQuaternions() + integratePosition() per rod (stages 1-2 only; the "
+                          "reference repeats the quaternion solve inside integratePosition), Eigen replaced by oracle/eigen_shim"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def cpu_baseline(target_seconds: float):
     o, how = _native_oracle()
     cores = _host_cores()
@@ -111,6 +131,7 @@ def cpu_baseline(target_seconds: float):
     value = sample / dt
     dt1 = _time_oracle(o, max(probe // cores, 64), 0, True, 1)
     dt_lu = _time_oracle(o, probe * 4, 0, False, cores)
+    ref_own = _reference_own_code_rate()
     return {
         "value": value, "unit": "rods/s", "cores": cores, "kind": "port",
         "sample": f"{sample} rods of the same Philox stream (rods 0..{sample - 1}), all four stages, explicit 60x60 "
@@ -118,6 +139,7 @@ def cpu_baseline(target_seconds: float):
         "value_1core": max(probe // cores, 64) / dt1,
         "value_lu_solve_variant": probe * 4 / dt_lu,
         "seconds": dt,
+        "reference_own_code_1core": ref_own,
     }
 
 

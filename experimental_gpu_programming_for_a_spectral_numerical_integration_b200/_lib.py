@@ -97,6 +97,8 @@ SYMBOLS = {
                                         c_int, c_double, c_int64, ALLREDUCE_FN, c_void_p, POINTER(NewtonReport)]),
     "sri_generate_rods": (c_int, [c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_last_error_string": (c_char_p, []),
+    "sri_set_timing": (c_int, [c_void_p, c_int]),
+    "sri_get_last_timing": (c_int, [c_void_p, POINTER(ctypes.c_float), POINTER(c_char_p)]),
     "sri_kernel_launch_count": (c_int64, []),
     "sri_get_handback_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "sri_measure_fp64_peak": (c_int, [c_void_p, POINTER(c_double)]),

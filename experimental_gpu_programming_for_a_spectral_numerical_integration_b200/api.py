@@ -421,6 +421,17 @@ class SpectralRodIntegrator:
             "sri_generate_rods",
         )
 
+    def set_timing(self, enabled: bool = True) -> None:
+        """CUDA-event timer around every following call on this handle (sri_set_timing)."""
+        _lib.check(self._lib.sri_set_timing(self._h, 1 if enabled else 0), "sri_set_timing")
+
+    def last_timing(self):
+        """(milliseconds on the device, entry point name) of the most recent timed call."""
+        ms = ctypes.c_float()
+        name = ctypes.c_char_p()
+        _lib.check(self._lib.sri_get_last_timing(self._h, ctypes.byref(ms), ctypes.byref(name)), "sri_get_last_timing")
+        return float(ms.value), (name.value.decode() if name.value else "")
+
     def handback_count(self) -> int:
         """Rods of the last device-buffer call that the DMMA elimination handed back to the row-pivoting kernel."""
         v = ctypes.c_int64()

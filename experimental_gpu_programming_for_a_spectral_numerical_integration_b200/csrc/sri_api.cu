@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 
 #include <algorithm>
 #include <atomic>
@@ -114,6 +115,11 @@ struct sri_context {
     size_t gtma_smem[3] = {0, 0, 0};  // the same for the 17 <= N <= 64 TMA stage kernels
     int gtma_occ[3] = {0, 0, 0};
     cudaEvent_t pipe_event = nullptr;  // orders the host-buffer pipeline after the work already queued on `stream`
+    // tracing: every API call is an NVTX range; with sri_set_timing a CUDA-event pair brackets its work on `stream`
+    bool timing = false;
+    int call_depth = 0;                // nested entry points (e.g. sri_integrate_quaternions -> sri_integrate_all) time once
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    const char* timed_call = nullptr;
     int stage_impl = 0;          // N <= 16 separate-stage entry points: 0 = measured best per stage (position, couple: TMA-staged;
                                  // stress: direct loads), 1 = SRI_STAGE_IMPL=tma everywhere, 2 = SRI_STAGE_IMPL=ldg everywhere       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
     // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
@@ -235,9 +241,37 @@ private:
     int prev_ = -1;
     bool restore_ = false;
 };
-#define SRI_ENTER(h)          \
-    DeviceGuard guard__;      \
-    SRI_TRY(guard__.enter(h))
+// One API call on a handle: device guard + NVTX range named after the entry point + (optional) CUDA-event timer.
+class CallScope {
+public:
+    explicit CallScope(const char* name) : name_(name) { nvtxRangePushA(name); }
+    CallScope(const CallScope&) = delete;
+    CallScope& operator=(const CallScope&) = delete;
+    int enter(sri_context* h) {
+        SRI_TRY(guard_.enter(h));
+        h_ = h;
+        if (h->call_depth++ == 0 && h->timing && h->t0) {
+            timed_ = cudaEventRecord(h->t0, h->stream) == cudaSuccess;
+            if (timed_) h->timed_call = nullptr;
+        }
+        return SRI_OK;
+    }
+    ~CallScope() {
+        if (h_) {
+            if (--h_->call_depth == 0 && timed_ && cudaEventRecord(h_->t1, h_->stream) == cudaSuccess) h_->timed_call = name_;
+        }
+        nvtxRangePop();
+    }
+
+private:
+    const char* name_;
+    DeviceGuard guard_;
+    sri_context* h_ = nullptr;
+    bool timed_ = false;
+};
+#define SRI_ENTER(h)               \
+    CallScope scope__(__func__);   \
+    SRI_TRY(scope__.enter(h))
 
 }  // namespace
 
@@ -852,6 +886,8 @@ int sri_destroy(sri_handle h) {
     if (h->d_wrench_scratch) cudaFree(h->d_wrench_scratch);
     if (h->d_gather) cudaFree(h->d_gather);
     if (h->pipe_event) cudaEventDestroy(h->pipe_event);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
     if (h->newton.host_state) cudaFreeHost(h->newton.host_state);
     for (cudaEvent_t e : h->newton.ev) if (e) cudaEventDestroy(e);
     if (h->d_ops16) cudaFree(h->d_ops16);
@@ -886,6 +922,28 @@ int sri_set_stream(sri_handle h, void* cuda_stream) {
 int sri_reset_stream(sri_handle h) {
     SRI_ENTER(h);
     h->stream = h->own_stream;
+    return SRI_OK;
+}
+
+int sri_set_timing(sri_handle h, int enabled) {
+    SRI_ENTER(h);
+    if (enabled && !h->t0) {
+        SRI_CUDA(cudaEventCreate(&h->t0));
+        SRI_CUDA(cudaEventCreate(&h->t1));
+    }
+    h->timing = enabled != 0;
+    h->timed_call = nullptr;
+    return SRI_OK;
+}
+
+int sri_get_last_timing(sri_handle h, float* ms, const char** entry_point) {
+    if (!h || !ms) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_last_timing: null argument");
+    DeviceGuard guard;
+    SRI_TRY(guard.enter(h));
+    if (!h->timing || !h->timed_call) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_last_timing: no timed call yet (sri_set_timing(h, 1) first)");
+    SRI_CUDA(cudaEventSynchronize(h->t1));
+    SRI_CUDA(cudaEventElapsedTime(ms, h->t0, h->t1));
+    if (entry_point) *entry_point = h->timed_call;
     return SRI_OK;
 }
 

@@ -276,6 +276,14 @@ int sri_generate_rods(sri_handle h, uint64_t seed, int64_t first_rod, int64_t ba
 /* ---- diagnostics -------------------------------------------------------------------------------------- */
 
 const char* sri_last_error_string(void);
+/* Tracing.  Every entry point that takes a handle is an NVTX range named after itself (nvtx3, header only:
+ * free unless a profiler is attached).  sri_set_timing(h, 1) additionally brackets the work of every following call on this
+ * handle with a CUDA-event pair on the handle's stream; sri_get_last_timing returns the device time of the most recent
+ * such call in milliseconds and the name of its entry point (waits for that call to finish).  The separate-stage entry
+ * points (sri_integrate_position / _stress / _couple, ...) are thereby timed stage by stage; the fused sri_integrate_all
+ * is one launch and one number. */
+int sri_set_timing(sri_handle h, int enabled);
+int sri_get_last_timing(sri_handle h, float* ms, const char** entry_point);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t sri_kernel_launch_count(void);
 /* N <= 16: the elimination runs on the FP64 tensor cores in static pivot order; a rod whose sub-diagonal growth

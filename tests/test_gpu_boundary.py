@@ -184,6 +184,40 @@ def test_caller_device_is_restored(h16, torch_mod):
         torch_mod.cuda.set_device(0)
 
 
+def test_per_call_event_timers_and_nvtx_ranges(sri_lib, oracle16, torch_mod):
+    """CUDA-event timers around each stage.  sri_set_timing brackets every call on the handle; the
+    separate-stage entry points are thereby timed stage by stage, nested entry points (sri_integrate_quaternions ->
+    sri_integrate_all) report the outer name once.  (The NVTX ranges are pushed unconditionally; they need a profiler to
+    be seen, here we only check that pushing them is harmless.)"""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator, SriError
+    B = 20000
+    K, F, Mt, fb = oracle16.generate_rods(0x5EED, 0, B)
+    t = lambda a: torch_mod.from_numpy(a).cuda()
+    with SpectralRodIntegrator(16, 0) as h:
+        with pytest.raises(SriError):
+            h.last_timing()  # timing is off by default
+        h.set_timing(True)
+        with pytest.raises(SriError):
+            h.last_timing()  # nothing timed yet
+        dK, dF, dM, dfb = t(K), t(F), t(Mt), t(fb)
+        seen = {}
+        Q = h.integrate_quaternions(dK); seen["sri_integrate_quaternions"] = h.last_timing()
+        r = h.integrate_position(Q); seen["sri_integrate_position"] = h.last_timing()
+        n = h.integrate_stress(dF, fbar=dfb); seen["sri_integrate_stress"] = h.last_timing()
+        m = h.integrate_couple(Q, n, dM); seen["sri_integrate_couple"] = h.last_timing()
+        h.integrate_all(dK, dF, dM, fbar=dfb); seen["sri_integrate_all"] = h.last_timing()
+        for name, (ms, got) in seen.items():
+            assert got == name and 0.0 < ms < 50.0, (name, ms, got)
+        # the quaternion stage is the expensive one (FP64-bound), the others stream
+        assert seen["sri_integrate_quaternions"][0] > seen["sri_integrate_position"][0]
+        h.set_timing(False)
+        h.integrate_position(Q)
+        with pytest.raises(SriError):
+            h.last_timing()
+        ref = oracle16.integrate_all(K[:100], F[:100], Mt[:100], fbar=fb[:100])
+        assert rel_err(m[:100].cpu().numpy(), ref["m"]) <= TOL and rel_err(r[:100].cpu().numpy(), ref["r"]) <= TOL
+
+
 # ---- several devices in one process -------------------------------------------------------------------------------------
 
 def test_multi_device_host_path_is_bit_identical_to_one_handle(h16, oracle16, torch_mod):
