@@ -1058,6 +1058,7 @@ int sri_integrate_all(sri_handle h, const sri_rod_batch* rods) {
 }
 
 int sri_integrate_quaternions(sri_handle h, int64_t batch, const double* K, const double* q0, double* Q, int* info) {
+    SRI_ENTER(h);  // (its own NVTX range and timer; the nested sri_integrate_all does not time again)
     if (batch > 0 && !Q) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_integrate_quaternions: Q == NULL");
     sri_rod_batch rb{};
     rb.batch = batch; rb.K = K; rb.q0 = q0; rb.Q = Q; rb.info = info;
