@@ -66,6 +66,7 @@ SYMBOLS = {
     "sri_get_operator": (c_int, [c_void_p, c_int, c_void_p]),
     "sri_strain_from_modes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "sri_assemble_A": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "sri_scale_for_length": (c_int, [c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sri_device_count": (c_int, [POINTER(c_int)]),
     "sri_create_multi": (c_int, [c_int, POINTER(c_int), c_int, POINTER(c_void_p)]),
     "sri_destroy_multi": (c_int, [c_void_p]),

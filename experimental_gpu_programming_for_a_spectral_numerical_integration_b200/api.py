@@ -183,6 +183,17 @@ class SpectralRodIntegrator:
         _lib.check(self._lib.sri_strain_from_modes(self._h, batch, ne, _ptr(qe, "qe"), _ptr(K, "K")), "sri_strain_from_modes")
         return K
 
+    def scale_for_length_(self, length, K=None, Gamma=None, fbar=None, lbar=None) -> None:
+        """sri_scale_for_length: scales the given [batch][3][N] arrays IN PLACE by the rod length (a float, or one value per rod as
+        an array / tensor).  See scale_for_length() for the out-of-place convenience form."""
+        ref = next(a for a in (K, Gamma, fbar, lbar) if a is not None)
+        self._follow_torch(ref)
+        batch = ref.shape[0]
+        per_rod = np.ndim(length) > 0 or _is_torch(length)
+        _lib.check(self._lib.sri_scale_for_length(self._h, batch, _ptr(length, "length") if per_rod else None,
+                                                  1.0 if per_rod else float(length), _ptr(K, "K"), _ptr(Gamma, "Gamma"),
+                                                  _ptr(fbar, "fbar"), _ptr(lbar, "lbar")), "sri_scale_for_length")
+
     def assemble_A(self, K, out=None):
         """A_NN [batch][4M][4M] of updateA (main.cpp:55-88), returned row/column indexed as A[b, row, col]."""
         self._follow_torch(K)

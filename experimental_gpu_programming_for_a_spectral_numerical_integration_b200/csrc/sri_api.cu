@@ -182,6 +182,8 @@ public:
         used_host_ = true;
         return SRI_OK;
     }
+    // an in-out host array that went in through in(): copy the staged device buffer back at finish()
+    void copy_back(void* host, void* dev, size_t bytes) { backs_.push_back({host, dev, bytes}); }
     int finish() {
         for (auto& b : backs_) SRI_CUDA(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, h_->stream));
         if (used_host_) SRI_CUDA(cudaStreamSynchronize(h_->stream));
@@ -1001,6 +1003,33 @@ int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe,
     SRI_TRY(st.in(qe, (size_t)batch * 3 * ne, &dqe));
     SRI_TRY(st.out(K, (size_t)batch * 3 * h->N, &dK));
     SRI_TRY(strain_from_modes_dev(h, batch, ne, dqe, dK));
+    return st.finish();
+}
+
+int sri_scale_for_length(sri_handle h, int64_t batch, const double* length, double uniform_length, double* K, double* Gamma,
+                         double* fbar, double* lbar) {
+    SRI_ENTER(h);
+    if (batch < 0) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_scale_for_length: negative batch");
+    if (batch == 0) return SRI_OK;
+    const int per_rod = 3 * h->N;
+    Staging st(h);
+    const double* dl = nullptr;
+    SRI_TRY(st.in(length, (size_t)batch, &dl));
+    double* arr[4] = {K, Gamma, fbar, lbar};
+    double* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i) {
+        if (!arr[i]) continue;
+        if (is_device_pointer(arr[i])) { dev[i] = arr[i]; continue; }
+        const double* in = nullptr;   // host array: in-out through a staged copy
+        SRI_TRY(st.in(arr[i], (size_t)batch * per_rod, &in));
+        dev[i] = const_cast<double*>(in);
+        st.copy_back(arr[i], dev[i], (size_t)batch * per_rod * sizeof(double));
+    }
+    const long long total = (long long)batch * per_rod;
+    scale_for_length_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16), 256, 0, h->stream>>>(
+        batch, per_rod, dl, uniform_length, dev[0], dev[1], dev[2], dev[3]);
+    g_launches.fetch_add(1);
+    SRI_CUDA(cudaGetLastError());
     return st.finish();
 }
 

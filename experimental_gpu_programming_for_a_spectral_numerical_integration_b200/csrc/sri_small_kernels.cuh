@@ -587,6 +587,22 @@ __global__ void __launch_bounds__(64) solve_small_reg_kernel(long long batch, co
     for (int e = 0; e < NN; ++e) xs[e] = r[e];
 }
 
+// x[b][...] *= length[b] (or the one length `uniform` when `length` is NULL) for up to four [batch][per_rod] arrays: the
+// input scaling that maps a rod of length l onto the unit-interval integrators (rod_modeling.pdf eq. 2.17).
+__global__ void scale_for_length_kernel(long long batch, int per_rod, const double* __restrict__ length, double uniform,
+                                        double* __restrict__ a0, double* __restrict__ a1, double* __restrict__ a2,
+                                        double* __restrict__ a3) {
+    const long long total = batch * per_rod;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const double l = length ? length[idx / per_rod] : uniform;
+        if (a0) a0[idx] *= l;
+        if (a1) a1[idx] *= l;
+        if (a2) a2[idx] *= l;
+        if (a3) a3[idx] *= l;
+    }
+}
+
 // SURVEY 8(d) synthetic rods.  One thread per rod.
 __global__ void generate_rods_kernel(unsigned long long seed, long long first_rod, long long batch, int N,
                                      const double* __restrict__ tnodes, double* __restrict__ K,

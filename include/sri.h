@@ -80,6 +80,15 @@ int sri_get_operator(sri_handle h, int which, double* out);
 /* K = Phi<3,ne>(x_i) * qe at every node (main.cpp:69).  qe [batch][3*ne] -> K [batch][3][N]. */
 int sri_strain_from_modes(sri_handle h, int64_t batch, int ne, const double* qe, double* K);
 
+/* Rod length.  The reference integrates on X in [0,1] with an implicit length of 1 (ComputeChebyshevPoints<N, 1>,
+ * main.cpp:15).  For a rod of length l every ODE is multiplied by l (rod_modeling.pdf eq. 2.17): Q' = l/2 Q (x) (0,K),
+ * r' = l R Gamma, n' = -l fbar, m' = -(r' x n + l lbar) -- i.e. the integrators are called with (l K, l Gamma, l fbar, l lbar),
+ * tip loads and outputs unchanged.  This scales the given [batch][3][N] arrays IN PLACE (any of them may be NULL; host or
+ * device pointers) by length[b] ([batch], host or device) or, when length == NULL, by uniform_length.  A rod with the
+ * default Gamma = (1,0,0) needs an explicit Gamma array holding (1,0,0) at every node before the call. */
+int sri_scale_for_length(sri_handle h, int64_t batch, const double* length, double uniform_length, double* K, double* Gamma,
+                         double* fbar, double* lbar);
+
 /* updateA()  main.cpp:55-88 on D_NN = I4 (x) Dn_NN (main.cpp:98,102): the assembled collocation operator of stage 1,
  * A_NN = D_NN - 1/2 blockdiag A(K_i), as the reference holds it before A_NN.inverse() (main.cpp:113).  The integration
  * kernels never form it (they eliminate the left-preconditioned quaternion system in registers); this entry point exists so

@@ -347,6 +347,15 @@ def test_rod_length_scaling(sri_lib, make_oracle, torch_mod, N, ell):
     sK, sG, sf, sl = scale_for_length(ell, K, Gam, fb, lb)
     with SpectralRodIntegrator(N, 0) as h:
         got = {k: v.cpu().numpy() for k, v in h.integrate_all(t(sK), t(F), t(Mt), Gamma=t(sG), fbar=t(sf), lbar=t(sl)).items()}
+        # the C-ABI form (sri_scale_for_length) scales in place: device tensors with one length per rod, host arrays with a scalar
+        dK, dG, df, dl = t(K), t(Gam), t(fb), t(lb)
+        h.scale_for_length_(torch_mod.full((B,), ell, dtype=torch_mod.float64, device="cuda"), dK, dG, df, dl)
+        h.synchronize()
+        for got_t, want in ((dK, sK), (dG, sG), (df, sf), (dl, sl)):
+            assert np.array_equal(got_t.cpu().numpy(), want)
+        hK, hf = K.copy(), fb.copy()
+        h.scale_for_length_(ell, K=hK, fbar=hf)
+        assert np.array_equal(hK, sK) and np.array_equal(hf, sf)
     D = o.dn() / ell  # d/ds on [0, ell]
     for b in range(B):
         A = np.kron(np.eye(4), D[:M, :M])
