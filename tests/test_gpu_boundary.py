@@ -380,3 +380,57 @@ def test_rod_length_scaling(sri_lib, make_oracle, torch_mod, N, ell):
         rhs = -(np.cross(rp[:, 1:].T, n) + lb[b][:, 1:].T) - np.outer(D[1:, 0], Mt[b])
         m = np.linalg.solve(D[1:, 1:], rhs)
         assert np.abs(m.T - got["m"][b]).max() <= 1e-10 * max(1.0, np.abs(m).max())
+
+
+# ---- two ranks, two GPUs: the NCCL hook end to end (skipped on one-GPU boxes) -----------------------------------------------
+
+def _nccl_rank(rank, world, id_path, out_path, B, ne):
+    import time
+
+    import torch
+
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator, shard_range
+    torch.cuda.set_device(rank)
+    h = SpectralRodIntegrator(16, rank)
+    if rank == 0:
+        uid = h.nccl_unique_id()
+        Path(id_path + ".tmp").write_bytes(uid)
+        Path(id_path + ".tmp").rename(id_path)
+    else:
+        while not Path(id_path).exists():
+            time.sleep(0.01)
+        uid = Path(id_path).read_bytes()
+    h.nccl_init(world, rank, uid)
+    lo, hi = shard_range(B, rank, world)
+    F = torch.zeros((hi - lo, 3), dtype=torch.float64, device=f"cuda:{rank}")
+    F[:, 2] = -torch.linspace(0.1, 2.0, B, dtype=torch.float64)[lo:hi].to(F.device)
+    Mt = torch.zeros_like(F)
+    qe, rep = h.newton_static_shape(F, Mt, ne, (1.0, 1.0, 0.77), fd_step=0.0, total_dof=3 * ne * B)
+    norms = torch.tensor([float(rank + 1), float(10 - rank)], dtype=torch.float64, device=f"cuda:{rank}")
+    h.nccl_allreduce_norms(norms)
+    h.synchronize()
+    np.savez(out_path + f".{rank}.npz", qe=qe.cpu().numpy(), hist=np.array(rep["rms_history"]), it=rep["iterations"],
+             conv=rep["converged"], norms=norms.cpu().numpy())
+    h.nccl_finalize()
+    h.close()
+
+
+def test_nccl_norm_reduction_two_ranks(sri_lib, h16, torch_mod, tmp_path):
+    """sri_nccl_init over two ranks (one process per GPU, the unique id exchanged through a file): the sharded Newton solve
+    takes the steps of the single-rank solve, both ranks see the same residual history, and sri_nccl_allreduce_norms is
+    (sum, max) over the ranks."""
+    if torch_mod.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    B, ne = 4001, 3
+    id_path, out_path = str(tmp_path / "nccl_id"), str(tmp_path / "out")
+    mp.spawn(_nccl_rank, args=(2, id_path, out_path, B, ne), nprocs=2, join=True)
+    parts = [np.load(out_path + f".{r}.npz") for r in range(2)]
+    F = torch_mod.zeros((B, 3), dtype=torch_mod.float64, device="cuda"); F[:, 2] = -torch_mod.linspace(0.1, 2.0, B, dtype=torch_mod.float64)
+    q1, rep1 = h16.newton_static_shape(F, torch_mod.zeros_like(F), ne, (1.0, 1.0, 0.77), fd_step=0.0)
+    assert all(bool(p["conv"]) for p in parts) and all(int(p["it"]) == rep1["iterations"] for p in parts)
+    assert np.array_equal(parts[0]["hist"], parts[1]["hist"])            # folded in rank order: identical bits on every rank
+    assert np.allclose(parts[0]["hist"], rep1["rms_history"], rtol=1e-9, atol=1e-18)
+    assert np.array_equal(np.concatenate([p["qe"] for p in parts]), q1.cpu().numpy())
+    for p in parts:
+        assert p["norms"].tolist() == [3.0, 10.0]
