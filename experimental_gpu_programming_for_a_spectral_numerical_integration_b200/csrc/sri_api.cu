@@ -104,7 +104,7 @@ struct sri_context {
         double *K, *Q, *m, *nn, *g0, *J, *delta, *qe, *red, *F, *Mt, *K0, *qw, *Kw, *Qw, *mw, *gw, *Fw, *Mtw, *K0w;
         int* sinfo = nullptr;            // [B] zero-pivot report of the per-rod Newton solve
         sri::NewtonState* state = nullptr;       // device: convergence flag, singular count, norm history
-        sri::NewtonState* host_state = nullptr;  // pinned mirror, filled by an asynchronous copy after every test
+        sri::NewtonState* host_state = nullptr;  // two pinned mirrors: test t is copied to mirror t & 1 (followed by event t & 1)
         cudaEvent_t ev[2] = {nullptr, nullptr};
     } newton;
     double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
@@ -1625,7 +1625,7 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         ws.sinfo = reinterpret_cast<int*>(ws.block + off);
         ws.B = B; ws.ne = ne; ws.has_K0 = k0; ws.analytic = analytic;
     }
-    if (!ws.host_state) SRI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ws.host_state), sizeof(NewtonState)));
+    if (!ws.host_state) SRI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ws.host_state), 2 * sizeof(NewtonState)));
     for (cudaEvent_t& e : ws.ev)
         if (!e) SRI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaStream_t st = h->stream;
@@ -1682,7 +1682,7 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         newton_check_kernel<<<1, 32, 0, st>>>(h->d_gather, nranks, dof, tol, ws.state);
         g_launches.fetch_add(1);
         SRI_CUDA(cudaGetLastError());
-        SRI_CUDA(cudaMemcpyAsync(ws.host_state, ws.state, sizeof(NewtonState), cudaMemcpyDeviceToHost, st));
+        SRI_CUDA(cudaMemcpyAsync(ws.host_state + (t & 1), ws.state, sizeof(NewtonState), cudaMemcpyDeviceToHost, st));
         SRI_CUDA(cudaEventRecord(ws.ev[t & 1], st));
         return SRI_OK;
     };
@@ -1691,6 +1691,7 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
     if (B > 0) SRI_TRY(evaluate(B, ws.qe, ws.K, ws.Q, ws.m, ws.F, ws.Mt, ws.K0, ws.g0, ws.red, analytic ? ws.nn : nullptr));
     rep.integrations = 1;
     unsigned long long singular = 0;
+    int last_mirror = 0;
     if (lagged) {
         SRI_TRY(test(0));
         for (int it = 0;; ++it) {
@@ -1698,11 +1699,12 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
             if (it < max_iter) {
                 SRI_TRY(iterate());
                 SRI_TRY(test(it + 1));
+                last_mirror = (it + 1) & 1;
             }
-            // The mirror is overwritten by the copy of test it+1, which may already have run: every entry it holds is final
-            // once written (hist[t] never changes, done only rises), so reading after event `it` is safe either way.
+            // test `it` was copied to mirror it & 1; the next copy into that mirror (test it + 2) is only enqueued in the next
+            // pass of this loop, after the read below
             SRI_CUDA(cudaEventSynchronize(ws.ev[it & 1]));
-            const volatile NewtonState* hs = ws.host_state;
+            const NewtonState* hs = ws.host_state + (it & 1);
             const double s2 = hs->hist[it][0], mx = hs->hist[it][1];
             rep.rms = dof > 0 ? std::sqrt(s2 / dof) : 0.0;
             rep.max_abs = mx;
@@ -1713,7 +1715,8 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
             rep.integrations += analytic ? 1 : n + 1;
         }
         SRI_CUDA(cudaStreamSynchronize(st));
-        singular = ws.host_state->singular;  // the last copy has landed
+        // every copy has landed; the newest state is in the mirror of the last test that was enqueued
+        singular = ws.host_state[last_mirror].singular;
     } else {
         for (int it = 0;; ++it) {
             double red[2] = {0.0, 0.0};
