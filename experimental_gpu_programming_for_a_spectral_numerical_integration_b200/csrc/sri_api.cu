@@ -1275,7 +1275,8 @@ static int galerkin_residual_dev(sri_context* h, int64_t batch, int ne, const do
                                  double* dred) {
     const int N = h->N;
     const int G = N <= 16 ? 16 : 32;
-    const long long blocks = ((long long)batch * G + 255) / 256;
+    const long long chunks = ((long long)batch * G + 255) / 256;
+    const long long blocks = std::min<long long>(chunks, (long long)h->sm_count * 4);  // persistent: 4 resident blocks per SM
     if (dred) {
         if (!h->d_counter) {
             SRI_CUDA(cudaMalloc(&h->d_counter, sizeof(unsigned)));
