@@ -31,6 +31,7 @@
 #include "sri_tiled.cuh"
 #include "sri_tiled_dmma.cuh"
 #include "sri_wrench_generic.cuh"
+#include "sri_wrench_gj.cuh"
 #include "sri_wrench_solve.cuh"
 
 // <row tiles per warp, column tiles, warps> of the N <= 32 instantiation of the multi-warp DMMA kernel
@@ -86,6 +87,8 @@ struct sri_context {
     double* d_wrench_scratch = nullptr;  // 58 <= N <= 64: per-CTA operator of sri_integrate_wrench_local (L2-resident)
     size_t wrench_scratch_cap = 0;
     int wrench_gen_occ = 0;
+    int wrench_gj_occ = 0;
+    int wrench_impl = 0;         // N <= 16: 0 = register-resident rolled Gauss-Jordan (default), 1 = SRI_WRENCH_IMPL=blocked (shared-memory blocked LU with DMMA)
     int jac_occ[9] = {};         // resident CTAs per SM of shape_jacobian_dmma_kernel<ne>
     int jac_impl = 0;            // 0: DMMA kernel for N <= 16 (default), 1: SRI_JACOBIAN_IMPL=scalar everywhere (A/B measurements)
     const int* skip = nullptr;   // Newton loop with the device-side convergence flag: kernels launched while this is set take
@@ -864,6 +867,7 @@ int sri_create(int N, int device, sri_handle* out) {
         const char* impl = std::getenv("SRI_FUSED16_IMPL");
         h->use_dmma = !(impl && std::strcmp(impl, "scalar") == 0);
         if (const char* si = std::getenv("SRI_STAGE_IMPL")) h->stage_impl = std::strcmp(si, "tma") == 0 ? 1 : (std::strcmp(si, "ldg") == 0 ? 2 : 0);
+        if (const char* wi = std::getenv("SRI_WRENCH_IMPL")) h->wrench_impl = std::strcmp(wi, "blocked") == 0 ? 1 : 0;
         if (const char* ji = std::getenv("SRI_JACOBIAN_IMPL")) h->jac_impl = std::strcmp(ji, "scalar") == 0 ? 1 : 0;
         if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
     }
@@ -1256,6 +1260,16 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
             }
         }
         sri::wrench_local_solve_generic_kernel<<<grid, sri::kWrenchGenThreads, smem, h->stream>>>(p, h->d_wrench_scratch, in_smem ? 1 : 0);
+    } else if (h->wrench_impl == 0) {
+        // one rod per warp, the whole operator in registers: rolled Gauss-Jordan with implicit partial pivoting
+        SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_gj_kernel, h->device, sri::kWrenchGjSmem));
+        if (h->wrench_gj_occ == 0)
+            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->wrench_gj_occ, sri::wrench_local_solve_gj_kernel,
+                                                                   32 * sri::kWrenchGjWarps, sri::kWrenchGjSmem));
+        if (h->wrench_gj_occ < 1) return fail(SRI_ERR_CUDA, "sri_integrate_wrench_local: kernel does not fit on this device");
+        const long long want = (batch + sri::kWrenchGjWarps - 1) / sri::kWrenchGjWarps;
+        const long long cap = (long long)h->sm_count * h->wrench_gj_occ;
+        sri::wrench_local_solve_gj_kernel<<<(int)(want < cap ? want : cap), 32 * sri::kWrenchGjWarps, sri::kWrenchGjSmem, h->stream>>>(p);
     } else {
         SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_kernel, h->device, sri::kWrenchSmem));
         const long long want = (batch + sri::kWrenchWarps - 1) / sri::kWrenchWarps;
