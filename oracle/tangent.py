@@ -105,16 +105,18 @@ def jacobian_by_quadrature(oracle, qe, F_tip, M_tip, H_diag, ne: int):
     return jacobian_by_quadrature_from_state(out["Q"], out["n"], out["m"], M_tip, H, ne, P, w, S, S_T)
 
 
-def jacobian_by_quadrature_from_state(Q, nn, mm, M_tip, H, ne, P, w, S, S_T):
+def jacobian_by_quadrature_from_state(Q, nn, mm, M_tip, H, ne, P, w, S, S_T, q0=None, Gamma=None):
+    """q0 [B][4] (rotation of the base node, default identity) and Gamma [B][3][N] (default e1) as in sri_shape_jacobian."""
     B, _, M = Q.shape
     N, n = M + 1, 3 * ne
     e1 = np.array([1.0, 0.0, 0.0])
     J = np.empty((B, n, n))
     for b in range(B):
-        Rn = rotation(np.concatenate([Q[b].T, [[1.0, 0.0, 0.0, 0.0]]]))               # [N][3][3], base node = identity
+        qb = [1.0, 0.0, 0.0, 0.0] if q0 is None else q0[b]
+        Rn = rotation(np.concatenate([Q[b].T, [qb]]))                                  # [N][3][3], base node = q0
         mn = np.concatenate([[M_tip[b]], mm[b].T])                                     # node 0: M_tip
         nj = nn[b].T                                                                   # nodes 1..N-1
-        bn = Rn @ e1
+        bn = Rn @ e1 if Gamma is None else np.einsum("ikc,ci->ik", Rn, Gamma[b])
         for d in range(n):
             c, k = divmod(d, ne)
             dK = np.zeros((3, N)); dK[c] = P[k]

@@ -285,7 +285,7 @@ def test_cpp_host_drives_the_newton_solve(sri_lib):
     assert res.stdout.startswith("converged 1")
 
 
-@pytest.mark.parametrize("N,ne", [(16, 3), (16, 4), (9, 2), (32, 3)])
+@pytest.mark.parametrize("N,ne", [(16, 3), (16, 4), (9, 2), (32, 3), (16, 1), (16, 8), (12, 5), (5, 2), (16, 6), (13, 7)])
 def test_shape_jacobian_matches_the_restated_quadrature_formula(sri_lib, make_oracle, torch_mod, N, ne):
     """sri_shape_jacobian (solve-free analytic Jacobian) against oracle/tangent.py's restatement on the same stage outputs;
     that restatement is pinned on the CPU against the exact tangent of the discrete map and against central differences."""
@@ -311,9 +311,18 @@ def test_shape_jacobian_matches_the_restated_quadrature_formula(sri_lib, make_or
         J = h.shape_jacobian(t(ref["Q"]), t(ref["n"]), t(ref["m"]), t(Mt), ne, H)
         J_host = h.shape_jacobian(ref["Q"][:5], ref["n"][:5], ref["m"][:5], Mt[:5], ne, H)
         h.synchronize()
+        # optional inputs: rotation of the base node and a nodal Gamma (shearable rod)
+        q0 = rng.normal(size=(B, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+        Gam = np.tile(np.array([1.0, 0.04, -0.03])[None, :, None], (B, 1, N)) + 0.01 * rng.normal(size=(B, 3, N))
+        ref2 = o.integrate_all(K, F, Mt, q0=q0, Gamma=Gam, explicit_inverse=False, want=("Q", "n", "m"))
+        J2 = h.shape_jacobian(t(ref2["Q"]), t(ref2["n"]), t(ref2["m"]), t(Mt), ne, H, q0=t(q0), Gamma=t(Gam))
+        h.synchronize()
     scale = np.abs(J_ref).max()
     assert np.abs(J.cpu().numpy() - J_ref).max() <= 1e-12 * scale
     assert np.abs(J_host - J_ref[:5]).max() <= 1e-12 * scale
+    J2_ref = jacobian_by_quadrature_from_state(ref2["Q"], ref2["n"], ref2["m"], Mt, H, ne, P, ccw(N), np.linalg.inv(Dn[:M, :M]),
+                                               np.linalg.inv(Dn[1:, 1:]), q0=q0, Gamma=Gam)
+    assert np.abs(J2.cpu().numpy() - J2_ref).max() <= 1e-12 * np.abs(J2_ref).max()
 
 
 def test_newton_with_the_analytic_jacobian(h16, torch_mod):
