@@ -12,6 +12,7 @@ integrates its own contiguous rod-index range [rank*rods, (rank+1)*rods).
 
 Beside the headline the same run reports, under `other_configs`, the other BASELINE.json configurations:
   cfg2        10^4 rods on one GPU                                   (1 GPU only)
+  stages      the four stages through their separate entry points, each against its roof (1 GPU only)
   cfg3_strong ONE batch of 10^6 rods sharded by rod index over the N GPUs (strong scaling; N > 1)
   cfg4        10^5 rods at N = 32 and N = 64                         (1 GPU only)
   cfg5        Newton static shape solve of 10^5 tip-loaded rods sharded over the N GPUs, residual norms reduced by NCCL on
@@ -405,6 +406,45 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize(dev)
         other["cfg2"] = {"workload": "cfg2: 10^4 rods, N=16, 1 GPU (a single 2.8-wave launch; L2-resident after the first pass)",
                          "rods_per_s": Bs / (e2.elapsed_time(e3) / 50 * 1e-3), "us_per_launch": e2.elapsed_time(e3) / 50 * 1e3}
+
+    # ---- the four stages one by one (separate-stage entry points, device-resident), each against the roof that bounds it: stage 1
+    #      FP64 tensor pipe, stages 2-4 HBM; timed with the library's own per-call CUDA-event timer (sri_set_timing)
+    if side and world == 1:
+        try:
+            hbm = 6650.0
+            try:
+                hbm = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", hbm)
+            except Exception:
+                pass
+            h.set_timing(True)
+
+            def stage_ms(fn, reps=10):
+                for _ in range(3):
+                    fn()
+                tot = 0.0
+                for _ in range(reps):
+                    fn()
+                    tot += h.last_timing()[0]
+                return tot / reps
+
+            st = {}
+            ms = stage_ms(lambda: h.integrate_quaternions(K, out=Q))
+            st["quaternions"] = {"entry": "sri_integrate_quaternions", "ms": ms, "rods_per_s": B / ms * 1e3, "bound": "tensor",
+                                 "dense_count_tflops": B / ms * 1e3 * 151_200 * 1e-12, "frac_of_dmma_peak_dense": B / ms * 1e3 * 151_200 * 1e-12 / dmma_peak}
+            for name, fn, bytes_per_rod in (
+                    ("position", lambda: h.integrate_position(Q, out=r), (4 * M + 3 * M) * 8),
+                    ("stress", lambda: h.integrate_stress(F, fbar=fb, out=n), (3 * N + 3 + 3 * M) * 8),
+                    ("couple", lambda: h.integrate_couple(Q, n, Mt, out=m), (4 * M + 3 * M + 3 + 3 * M) * 8)):
+                ms = stage_ms(fn)
+                gbs = B * bytes_per_rod / ms * 1e-6
+                st[name] = {"entry": f"sri_integrate_{name}", "ms": ms, "rods_per_s": B / ms * 1e3, "bound": "hbm", "bytes_per_rod": bytes_per_rod,
+                            "GBps": gbs, "frac_of_hbm_peak": gbs / hbm}
+            h.set_timing(False)
+            st["note"] = ("separate-stage entry points on the headline batch; the fused sri_integrate_all (the headline) does all four in "
+                          "one launch and keeps Q on the SM; hbm peak = MEASURED_PEAKS.json copy bandwidth")
+            other["stages"] = st
+        except Exception as exc:  # noqa: BLE001
+            other["stages"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- BASELINE configs[2], the north-star target: ONE batch of 10^6 rods sharded by rod index over the GPUs (strong
     #      scaling), device-resident, same timing rules as the headline ------------------------------------------------
