@@ -186,7 +186,8 @@ int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double*
  * collocated with the tip node eliminated: the strain-dependent operator D_TT (x) I3 + blockdiag(K^_i) (3M x 3M), one
  * partial-pivot LU per rod and two solves.  Agrees with sri_wrench_local on the global-frame stages to the
  * discretisation error (1e-8 at N = 16, round-off from N = 32).  One rod per warp for N <= 16 (register-resident
- * Gauss-Jordan elimination with partial pivoting), one rod per CTA for 17 <= N <= 64.  K [batch][3][N]; Q [batch][4][M] from stage 1; optional inputs as
+ * Gauss-Jordan elimination with partial pivoting), one rod per CTA for 17 <= N <= 64 (the same elimination over 2-3 warps up to
+ * N = 33, a CTA-wide LU beyond).  K [batch][3][N]; Q [batch][4][M] from stage 1; optional inputs as
  * in sri_integrate_all; Lambda [batch][6][N], couple first; info [batch] or NULL (zero-pivot step of the LU). */
 int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, const double* Q, const double* q0,
                                const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
