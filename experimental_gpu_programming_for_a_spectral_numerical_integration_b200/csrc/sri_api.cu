@@ -89,7 +89,7 @@ struct sri_context {
     size_t wrench_scratch_cap = 0;
     int wrench_gen_occ = 0;
     int wrench_gj_occ = 0;
-    int wrench_impl = 0;         // 0 = register-resident rolled Gauss-Jordan (default, N <= 33), 1 = SRI_WRENCH_IMPL=blocked (N <= 16: shared-memory blocked LU with DMMA), 2 = SRI_WRENCH_IMPL=generic (N > 16: CTA-wide LU)
+    int wrench_impl = 0;         // SRI_WRENCH_IMPL: 0 = default (register-resident rolled Gauss-Jordan, N <= 33: one row per lane over 1-3 warps, two rows per lane for 12 <= N <= 16), 1 = blocked (N <= 16: shared-memory blocked LU with DMMA), 2 = generic (N > 16: CTA-wide LU), 3 = multi (one row per lane also for 12 <= N <= 16), 4 = warp (two rows per lane for every N <= 16)
     int jac_occ[9] = {};         // resident CTAs per SM of shape_jacobian_dmma_kernel<ne>
     int jac_impl = 0;            // 0: DMMA kernel for N <= 16 (default), 1: SRI_JACOBIAN_IMPL=scalar everywhere (A/B measurements)
     const int* skip = nullptr;   // Newton loop with the device-side convergence flag: kernels launched while this is set take
@@ -868,7 +868,7 @@ int sri_create(int N, int device, sri_handle* out) {
         const char* impl = std::getenv("SRI_FUSED16_IMPL");
         h->use_dmma = !(impl && std::strcmp(impl, "scalar") == 0);
         if (const char* si = std::getenv("SRI_STAGE_IMPL")) h->stage_impl = std::strcmp(si, "tma") == 0 ? 1 : (std::strcmp(si, "ldg") == 0 ? 2 : 0);
-        if (const char* wi = std::getenv("SRI_WRENCH_IMPL")) h->wrench_impl = std::strcmp(wi, "blocked") == 0 ? 1 : (std::strcmp(wi, "generic") == 0 ? 2 : 0);
+        if (const char* wi = std::getenv("SRI_WRENCH_IMPL")) h->wrench_impl = std::strcmp(wi, "blocked") == 0 ? 1 : (std::strcmp(wi, "generic") == 0 ? 2 : (std::strcmp(wi, "multi") == 0 ? 3 : (std::strcmp(wi, "warp") == 0 ? 4 : 0)));
         if (const char* ji = std::getenv("SRI_JACOBIAN_IMPL")) h->jac_impl = std::strcmp(ji, "scalar") == 0 ? 1 : 0;
         if (const char* gs = std::getenv("SRI_DMMA_GROWTH")) { const double gv = std::atof(gs); if (gv >= 0.0) h->dmma_growth = gv; }
     }
@@ -1217,6 +1217,25 @@ int sri_wrench_local(sri_handle h, int64_t batch, const double* Q, const double*
     return st.finish();
 }
 
+// one rod per CTA of NW warps (csrc/sri_wrench_gj_multi.cuh); grid = min(batch, resident CTAs)
+extern "C++" {
+namespace {
+template <int NW, int WMAX, int MINB>
+int launch_wrench_gjm(sri_context* h, const sri::WrenchParams& p, int64_t batch) {
+    using C = sri::WrenchGjMultiCfg<NW, WMAX>;
+    static_assert(C::NODES <= 33, "node capacity");
+    auto* kern = sri::wrench_local_solve_gj_multi_kernel<NW, WMAX, MINB>;
+    SRI_TRY(ensure_dynamic_smem(kern, h->device, C::smem_bytes));
+    int occ = 0;
+    SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NW, C::smem_bytes));
+    if (occ < 1) return fail(SRI_ERR_CUDA, "sri_integrate_wrench_local: kernel does not fit on this device");
+    const long long cap = (long long)h->sm_count * occ;
+    kern<<<(int)(batch < cap ? batch : cap), 32 * NW, C::smem_bytes, h->stream>>>(p);
+    return SRI_OK;
+}
+}  // namespace
+}  // extern "C++"
+
 int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, const double* Q, const double* q0,
                                const double* Gamma, const double* fbar, const double* lbar, const double* F_tip,
                                const double* M_tip, double* Lambda, int* info) {
@@ -1237,24 +1256,15 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &p.Lambda));
     SRI_TRY(st.out(info, (size_t)batch, &p.info));
-    if (N > 16 && N <= sri::WrenchGjMultiCfg<3>::NODES && h->wrench_impl != 2) {
-        // one rod per CTA of 2 or 3 warps, one operator row per lane in registers: the rolled Gauss-Jordan across warps
-        const bool two = N <= sri::WrenchGjMultiCfg<2>::NODES;
-        const size_t smem = two ? sri::WrenchGjMultiCfg<2>::smem_bytes : sri::WrenchGjMultiCfg<3>::smem_bytes;
-        const int threads = two ? 64 : 96;
-        int occ = 0;
-        if (two) {
-            SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_gj_multi_kernel<2>, h->device, smem));
-            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::wrench_local_solve_gj_multi_kernel<2>, threads, smem));
-        } else {
-            SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_gj_multi_kernel<3>, h->device, smem));
-            SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sri::wrench_local_solve_gj_multi_kernel<3>, threads, smem));
-        }
-        if (occ < 1) return fail(SRI_ERR_CUDA, "sri_integrate_wrench_local: kernel does not fit on this device");
-        const long long capm = (long long)h->sm_count * occ;
-        const int grid = (int)(batch < capm ? batch : capm);
-        if (two) sri::wrench_local_solve_gj_multi_kernel<2><<<grid, threads, smem, h->stream>>>(p);
-        else sri::wrench_local_solve_gj_multi_kernel<3><<<grid, threads, smem, h->stream>>>(p);
+    // register-resident rolled Gauss-Jordan, ONE operator row per lane, one rod per CTA of 1-3 warps (measured per N against
+    // the two-rows-per-lane single-warp kernel, which stays the default for 12 <= N <= 16)
+    if ((h->wrench_impl == 0 || h->wrench_impl == 3) && N <= 11) {
+        SRI_TRY((launch_wrench_gjm<1, 32, 16>(h, p, batch)));
+    } else if ((h->wrench_impl == 3 && N <= 17) || (h->wrench_impl == 0 && N == 17)) {
+        SRI_TRY((launch_wrench_gjm<2, 48, 6>(h, p, batch)));
+    } else if (N > 16 && N <= 33 && h->wrench_impl != 2) {
+        if (N <= 22) SRI_TRY((launch_wrench_gjm<2, 64, 5>(h, p, batch)));
+        else SRI_TRY((launch_wrench_gjm<3, 96, 1>(h, p, batch)));
     } else if (N > 16) {
         // one rod per CTA, dense 3M x 3M operator in shared memory while it fits (N <= 55), else in an L2-resident scratch
         const int n = 3 * M, ld = n | 1;
@@ -1279,7 +1289,7 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
             }
         }
         sri::wrench_local_solve_generic_kernel<<<grid, sri::kWrenchGenThreads, smem, h->stream>>>(p, h->d_wrench_scratch, in_smem ? 1 : 0);
-    } else if (h->wrench_impl == 0) {
+    } else if (h->wrench_impl != 1) {
         // one rod per warp, the whole operator in registers: rolled Gauss-Jordan with implicit partial pivoting
         SRI_TRY(ensure_dynamic_smem(sri::wrench_local_solve_gj_kernel, h->device, sri::kWrenchGjSmem));
         if (h->wrench_gj_occ == 0)

@@ -16,59 +16,61 @@
 
 namespace sri {
 
-template <int NW>
+template <int NW, int WMAX_ = 32 * NW>
 struct WrenchGjMultiCfg {
-    static constexpr int WMAX = 32 * NW;                 // rows (one per lane) and window slots
-    static constexpr int NODES = WMAX / 3 + 1;           // node capacity (N <= NODES): 22 / 33
+    static_assert(WMAX_ % 8 == 0 && WMAX_ <= 32 * NW, "window: a multiple of 8 slots, at most one per row");
+    static constexpr int ROWS = 32 * NW;                 // rows (one per lane)
+    static constexpr int WMAX = WMAX_;                   // window slots = unknowns the instantiation can hold
+    static constexpr int NODES = WMAX / 3 + 1;           // node capacity (N <= NODES): 17 / 22 / 33
     // shared memory, doubles
-    static constexpr int L = 0;                          // [WMAX][WMAX] multipliers by (step, row)
-    static constexpr int urow = L + WMAX * WMAX;         // [2][WMAX + 4] published pivot row: window, (RHS, 1/pivot) at WMAX
-    static constexpr int cand = urow + 2 * (WMAX + 4);   // [2][NW][4] arg-max posts: (hi word, lo word, row) as doubles
-    static constexpr int R = cand + 2 * NW * 4;          // [NODES][9]
+    static constexpr int L = 0;                          // [WMAX][ROWS] multipliers by (step, row)
+    static constexpr int urow = L + WMAX * ROWS;         // [2][WMAX + 4] published pivot row: window, (RHS, 1/pivot) at WMAX
+    static constexpr int cand = urow + 2 * (WMAX + 4);   // [2][NW] arg-max posts: int4 (hi word, lo word, row, -)
+    static constexpr int R = cand + 2 * NW * 2;          // [NODES][9]
     static constexpr int kk = R + 9 * NODES + (NODES & 1);  // [3][NODES]
     static constexpr int dti = kk + 3 * NODES + (NODES & 1);  // [NODES]
     static constexpr int vec = dti + NODES + (NODES & 1);  // [WMAX] couple solution by unknown index
     static constexpr int Nl = vec + WMAX;                // [WMAX] force solution by unknown index
     static constexpr int ysm = Nl + WMAX;                // [2] pivot value of the second sweep (double buffered)
-    static constexpr int piv = ysm + 2;                  // WMAX ints
-    static constexpr int total = piv + WMAX / 2;
+    static constexpr int total = ysm + 2;
     static constexpr size_t smem_bytes = (size_t)total * sizeof(double);
 };
 
-// this warp's best candidate -> the post slot of the warp (lane 0 writes)
-__device__ __forceinline__ void wrench_gjm_post(double a, bool used, int row, int lane, double* __restrict__ slot) {
+// this warp's best candidate (|a| as two words, row; row < 0: none left) -> the post slot of the warp (lane 0 writes; a
+// single-warp CTA needs no exchange and keeps it in registers)
+template <int NW>
+__device__ __forceinline__ void wrench_gjm_post(double a, bool used, int row, int lane, int* __restrict__ slot, unsigned& mh,
+                                                unsigned& ml, int& best) {
     constexpr unsigned FULL = 0xffffffffu;
     const double v = used ? 0.0 : fabs(a);
     const unsigned h = (unsigned)__double2hiint(v), l = (unsigned)__double2loint(v);
-    const unsigned mh = __reduce_max_sync(FULL, h);
-    const unsigned ml = __reduce_max_sync(FULL, h == mh ? l : 0u);
+    mh = __reduce_max_sync(FULL, h);
+    ml = __reduce_max_sync(FULL, h == mh ? l : 0u);
     const unsigned m = __ballot_sync(FULL, !used && h == mh && l == ml);
-    if (lane == 0) {
-        slot[0] = (double)mh; slot[1] = (double)ml;
-        slot[2] = m ? (double)((row & ~31) + __ffs(m) - 1) : -1.0;
-    }
+    best = m ? (row & ~31) + __ffs(m) - 1 : -1;
+    if (NW > 1 && lane == 0) *reinterpret_cast<int4*>(slot) = make_int4((int)mh, (int)ml, best, 0);
 }
 
 // best of the NW posts: exact comparison of (hi, lo), first (lowest) row on ties
 template <int NW>
-__device__ __forceinline__ void wrench_gjm_decide(const double* __restrict__ posts, int& prow, bool& singular) {
+__device__ __forceinline__ void wrench_gjm_decide(const int* __restrict__ posts, int& prow, bool& singular) {
     unsigned bh = 0u, bl = 0u;
     prow = -1;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-        const unsigned h = (unsigned)posts[4 * w], l = (unsigned)posts[4 * w + 1];
-        const int r = (int)posts[4 * w + 2];
+        const int4 post = *reinterpret_cast<const int4*>(posts + 4 * w);
+        const unsigned h = (unsigned)post.x, l = (unsigned)post.y;
+        const int r = post.z;
         if (r >= 0 && (prow < 0 || h > bh || (h == bh && l > bl))) { bh = h; bl = l; prow = r; }
     }
     singular = prow < 0 || (bh | bl) == 0u || bh >= 0x7ff00000u;
 }
 
-template <int NW, int W>
-__device__ __forceinline__ void wrench_gjm_body(double (&A)[32 * NW], double& rhs, int& k, const int n, const int row, bool& used,
+template <int NW, int WMAX, int W>
+__device__ __forceinline__ void wrench_gjm_body(double (&A)[WMAX], double& rhs, int& k, const int n, const int row, bool& used,
                                                 int& srow, int& bad, int& prow, bool& singular, double& rc,
                                                 double* __restrict__ sm, const int lane, const int warp) {
-    using C = WrenchGjMultiCfg<NW>;
-    constexpr int WMAX = C::WMAX;
+    using C = WrenchGjMultiCfg<NW, WMAX>;
 #pragma unroll 1
     for (int s = 0; s < 8 && k < n; ++s, ++k) {
         if (singular && !bad) bad = k + 1;
@@ -78,23 +80,24 @@ __device__ __forceinline__ void wrench_gjm_body(double (&A)[32 * NW], double& rh
 #pragma unroll
             for (int j = 0; j < W; j += 2) *reinterpret_cast<double2*>(ub + j) = make_double2(A[j], A[j + 1]);
             *reinterpret_cast<double2*>(ub + WMAX) = make_double2(rhs, rc);
-            reinterpret_cast<int*>(sm + C::piv)[k] = prow;
             used = true; srow = k;
         }
-        if (prow < 0 && lane == 0 && warp == 0) { reinterpret_cast<int*>(sm + C::piv)[k] = 0; *reinterpret_cast<double2*>(ub + WMAX) = make_double2(0.0, 0.0); }
+        if (prow < 0 && lane == 0 && warp == 0) *reinterpret_cast<double2*>(ub + WMAX) = make_double2(0.0, 0.0);
         __syncthreads();
         const double2 tail = *reinterpret_cast<const double2*>(ub + WMAX);   // (right-hand side of the pivot row, 1 / pivot)
         const double inv = singular ? 0.0 : tail.y;
         const double ml = mine ? 1.0 - inv : A[0] * inv;   // the pivot row is normalised by the same update
-        sm[C::L + k * WMAX + row] = ml;
+        sm[C::L + k * C::ROWS + row] = ml;
         // the next pivot column first: its candidates are posted before the bulk of the update
         {
             const double2 u = *reinterpret_cast<const double2*>(ub);
             A[0] = fma(-ml, u.y, A[1]);
         }
+        unsigned ph = 0u, pl = 0u;
+        int pbest = -1;
         if (k + 1 < n) {
             rc = fast_rcp(A[0]);
-            wrench_gjm_post(A[0], used, row, lane, sm + C::cand + (((k + 1) & 1) * NW + warp) * 4);
+            wrench_gjm_post<NW>(A[0], used, row, lane, reinterpret_cast<int*>(sm + C::cand) + (((k + 1) & 1) * NW + warp) * 4, ph, pl, pbest);
         }
 #pragma unroll
         for (int j = 2; j < W; j += 2) {
@@ -104,23 +107,26 @@ __device__ __forceinline__ void wrench_gjm_body(double (&A)[32 * NW], double& rh
         }
         A[W - 1] = 0.0;
         rhs = fma(-ml, tail.x, rhs);
-        __syncthreads();
-        if (k + 1 < n) wrench_gjm_decide<NW>(sm + C::cand + ((k + 1) & 1) * NW * 4, prow, singular);
+        if constexpr (NW == 1) {
+            if (k + 1 < n) { prow = pbest; singular = pbest < 0 || (ph | pl) == 0u || ph >= 0x7ff00000u; }
+        } else {
+            __syncthreads();
+            if (k + 1 < n) wrench_gjm_decide<NW>(reinterpret_cast<const int*>(sm + C::cand) + ((k + 1) & 1) * NW * 4, prow, singular);
+        }
     }
 }
 
-template <int NW, int W>
-__device__ __forceinline__ void wrench_gjm_bodies(double (&A)[32 * NW], double& rhs, int& k, const int n, const int row, bool& used,
+template <int NW, int WMAX, int W>
+__device__ __forceinline__ void wrench_gjm_bodies(double (&A)[WMAX], double& rhs, int& k, const int n, const int row, bool& used,
                                                   int& srow, int& bad, int& prow, bool& singular, double& rc,
                                                   double* __restrict__ sm, const int lane, const int warp) {
-    wrench_gjm_body<NW, W>(A, rhs, k, n, row, used, srow, bad, prow, singular, rc, sm, lane, warp);
-    if constexpr (W > 8) wrench_gjm_bodies<NW, W - 8>(A, rhs, k, n, row, used, srow, bad, prow, singular, rc, sm, lane, warp);
+    wrench_gjm_body<NW, WMAX, W>(A, rhs, k, n, row, used, srow, bad, prow, singular, rc, sm, lane, warp);
+    if constexpr (W > 8) wrench_gjm_bodies<NW, WMAX, W - 8>(A, rhs, k, n, row, used, srow, bad, prow, singular, rc, sm, lane, warp);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(32 * NW) wrench_local_solve_gj_multi_kernel(const WrenchParams p) {
-    using C = WrenchGjMultiCfg<NW>;
-    constexpr int WMAX = C::WMAX;
+template <int NW, int WMAX, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) wrench_local_solve_gj_multi_kernel(const WrenchParams p) {
+    using C = WrenchGjMultiCfg<NW, WMAX>;
     extern __shared__ __align__(16) double sm[];
     double* Rm = sm + C::R;
     double* kk = sm + C::kk;
@@ -128,7 +134,6 @@ __global__ void __launch_bounds__(32 * NW) wrench_local_solve_gj_multi_kernel(co
     double* vec = sm + C::vec;
     double* Nl = sm + C::Nl;
     double* ysm = sm + C::ysm;
-    const int* piv = reinterpret_cast<const int*>(sm + C::piv);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, M = p.M, n = 3 * M;
     const int row = tid;                       // row = (node row / 3 + 1, component row % 3)
@@ -187,10 +192,18 @@ __global__ void __launch_bounds__(32 * NW) wrench_local_solve_gj_multi_kernel(co
         bool used = !real, singular = false;
         int srow = WMAX, bad = 0, k = 0, prow = -1;
         double rc = fast_rcp(A[0]);
-        wrench_gjm_post(A[0], used, row, lane, sm + C::cand + warp * 4);
-        __syncthreads();
-        wrench_gjm_decide<NW>(sm + C::cand, prow, singular);
-        wrench_gjm_bodies<NW, WMAX>(A, rhs, k, n, row, used, srow, bad, prow, singular, rc, sm, lane, warp);
+        {
+            unsigned ph, pl;
+            int pbest;
+            wrench_gjm_post<NW>(A[0], used, row, lane, reinterpret_cast<int*>(sm + C::cand) + warp * 4, ph, pl, pbest);
+            if constexpr (NW == 1) {
+                prow = pbest; singular = pbest < 0 || (ph | pl) == 0u || ph >= 0x7ff00000u;
+            } else {
+                __syncthreads();
+                wrench_gjm_decide<NW>(reinterpret_cast<const int*>(sm + C::cand), prow, singular);
+            }
+        }
+        wrench_gjm_bodies<NW, WMAX, WMAX>(A, rhs, k, n, row, used, srow, bad, prow, singular, rc, sm, lane, warp);
         if (srow < WMAX) Nl[srow] = rhs;   // the row that was pivot at step s holds unknown s
         __syncthreads();
         // ---- internal couple through the stored multipliers ---------------------------------------------------------------------
@@ -205,11 +218,20 @@ __global__ void __launch_bounds__(32 * NW) wrench_local_solve_gj_multi_kernel(co
             if (p.lbar) { const double* l = p.lbar + rod * 3 * N + ri + 1; rl = Ri[0 * 3 + rc_comp] * l[0] + Ri[1 * 3 + rc_comp] * l[N] + Ri[2 * 3 + rc_comp] * l[2 * N]; }
             b = -gx - rl - dti[ri] * (rc_comp == 0 ? C0[0] : (rc_comp == 1 ? C0[1] : C0[2]));
         }
+        if constexpr (NW == 1) {
 #pragma unroll 1
-        for (int kq = 0; kq < n; ++kq) {
-            if (srow == kq) ysm[kq & 1] = b;   // the pivot row of step kq posts its current value
-            __syncthreads();
-            b = fma(-sm[C::L + kq * WMAX + row], ysm[kq & 1], b);
+            for (int kq = 0; kq < n; ++kq) {   // the pivot row of step kq hands its current value round by shuffle
+                const unsigned own = __ballot_sync(0xffffffffu, srow == kq);
+                const double y = own ? __shfl_sync(0xffffffffu, b, __ffs(own) - 1) : 0.0;
+                b = fma(-sm[C::L + kq * C::ROWS + row], y, b);
+            }
+        } else {
+#pragma unroll 1
+            for (int kq = 0; kq < n; ++kq) {
+                if (srow == kq) ysm[kq & 1] = b;   // the pivot row of step kq posts its current value
+                __syncthreads();
+                b = fma(-sm[C::L + kq * C::ROWS + row], ysm[kq & 1], b);
+            }
         }
         if (srow < WMAX) vec[srow] = b;
         __syncthreads();
@@ -225,7 +247,6 @@ __global__ void __launch_bounds__(32 * NW) wrench_local_solve_gj_multi_kernel(co
             out[(3 + c) * N + i + 1] = Nl[e];
         }
         if (p.info && tid == 0) p.info[rod] = bad;
-        (void)piv;
     }
 }
 
