@@ -33,6 +33,7 @@
 #include "sri_wrench_generic.cuh"
 #include "sri_wrench_gj.cuh"
 #include "sri_wrench_gj_multi.cuh"
+#include "sri_wrench_gj_static.cuh"
 #include "sri_wrench_solve.cuh"
 
 // <row tiles per warp, column tiles, warps> of the N <= 32 instantiation of the multi-warp DMMA kernel
@@ -78,7 +79,7 @@ struct sri_context {
     size_t generic_smem = 0;
     int generic_blocks_per_sm = 0;
     double* d_ops2 = nullptr;    // N > 16: tables of the DMMA kernel (Stx | AS | AT, TiledDmmaCfg)
-    double* d_dtt = nullptr;     // D_TT (M x M, column-major) followed by D_TI (M): operator of the local-frame statics solve
+    double* d_dtt = nullptr;     // D_TT (M x M, column-major), D_TI (M), D_TT^-1 (M x M): operator of the local-frame statics solve and its preconditioner
     double* d_tnodes = nullptr;  // 2 x_i - 1, i = 0..N-1
     double* d_reduce = nullptr;  // 2 doubles: sum rho^2, max |rho|
     double* d_ccw = nullptr;     // Clenshaw-Curtis weights of the nodes, [N]
@@ -127,8 +128,9 @@ struct sri_context {
     int stage_impl = 0;          // N <= 16 separate-stage entry points: 0 = measured best per stage (position, couple: TMA-staged;
                                  // stress: direct loads), 1 = SRI_STAGE_IMPL=tma everywhere, 2 = SRI_STAGE_IMPL=ldg everywhere       // N <= 16: DMMA elimination first, row-pivoting scalar kernel for the rods it hands back
     // rods handed back by the DMMA kernel: [0] = count, entries from [4]; one list per pipeline slot + the handle stream
-    int* d_list[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t list_cap[4] = {0, 0, 0, 0};
+    int* d_list[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // hand-back lists: pipeline slots 0-2, handle stream 3, local-frame statics 4
+    size_t list_cap[5] = {0, 0, 0, 0, 0};
+    int last_handback_slot = 3;  // list of the most recent two-pass call on the handle's stream (sri_get_handback_count)
     // host-buffer pipeline: chunks of rods flow H2D -> kernel -> D2H on rotating streams with persistent staging
     static constexpr int kPipeSlots = 3;
     static constexpr int kPipeArrays = 13;
@@ -308,6 +310,7 @@ int launch_generic(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
         p.rod_count = h->d_list[list_slot];
         p.rod_list = h->d_list[list_slot] + 4;
         SRI_CUDA(cudaMemsetAsync(p.rod_count, 0, sizeof(int), stream));
+        if (list_slot == 3) h->last_handback_slot = 3;
         const long long dcap = (long long)h->sm_count * h->dmma_blocks_per_sm;
         const int dgrid = (int)(p.batch < dcap ? p.batch : dcap);
         if (h->R == 32) {
@@ -374,6 +377,7 @@ int launch_fused16(sri_context* h, const sri::FusedParams& p_in, cudaStream_t st
             p.rod_count = h->d_list[list_slot];
             p.rod_list = h->d_list[list_slot] + 4;
             SRI_CUDA(cudaMemsetAsync(p.rod_count, 0, sizeof(int), stream));
+            if (list_slot == 3) h->last_handback_slot = 3;
             constexpr int wpc = sri::kDmmaThreads / 32;
             const long long dwant = (p.batch + wpc - 1) / wpc;
             const long long dcap = (long long)h->sm_count * h->dmma_blocks_per_sm;
@@ -834,9 +838,10 @@ int sri_create(int N, int device, sri_handle* out) {
         SRI_CUDA(cudaDeviceSynchronize());
     }
     {
-        std::vector<double> t((size_t)M * M + M);
+        std::vector<double> t((size_t)2 * M * M + M);   // D_TT, D_TI, D_TT^-1
         std::copy(h->ops.D_TT.begin(), h->ops.D_TT.end(), t.begin());
         std::copy(h->ops.D_TI.begin(), h->ops.D_TI.end(), t.begin() + (size_t)M * M);
+        std::copy(h->ops.ST.begin(), h->ops.ST.end(), t.begin() + (size_t)M * M + M);
         SRI_CUDA(cudaMalloc(&h->d_dtt, sizeof(double) * t.size()));
         SRI_CUDA(cudaMemcpy(h->d_dtt, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));
     }
@@ -908,7 +913,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->newton.block) cudaFree(h->newton.block);
-    for (int sl = 0; sl < 4; ++sl)
+    for (int sl = 0; sl < 5; ++sl)
         if (h->d_list[sl]) cudaFree(h->d_list[sl]);
     for (int sl = 0; sl < sri_context::kPipeSlots; ++sl) {
         for (int a = 0; a < sri_context::kPipeArrays; ++a)
@@ -1233,6 +1238,18 @@ int launch_wrench_gjm(sri_context* h, const sri::WrenchParams& p, int64_t batch)
     kern<<<(int)(batch < cap ? batch : cap), 32 * NW, C::smem_bytes, h->stream>>>(p);
     return SRI_OK;
 }
+template <int NW, int WMAX, int MINB>
+int launch_wrench_gjs(sri_context* h, const sri::WrenchParams& p, int64_t batch) {
+    using C = sri::WrenchGjStaticCfg<NW, WMAX>;
+    auto* kern = sri::wrench_local_solve_gj_static_kernel<NW, WMAX, MINB>;
+    SRI_TRY(ensure_dynamic_smem(kern, h->device, C::smem_bytes));
+    int occ = 0;
+    SRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NW, C::smem_bytes));
+    if (occ < 1) return fail(SRI_ERR_CUDA, "sri_integrate_wrench_local: kernel does not fit on this device");
+    const long long cap = (long long)h->sm_count * occ;
+    kern<<<(int)(batch < cap ? batch : cap), 32 * NW, C::smem_bytes, h->stream>>>(p);
+    return SRI_OK;
+}
 }  // namespace
 }  // extern "C++"
 
@@ -1256,8 +1273,31 @@ int sri_integrate_wrench_local(sri_handle h, int64_t batch, const double* K, con
     SRI_TRY(st.in(M_tip, (size_t)batch * 3, &p.M_tip));
     SRI_TRY(st.out(Lambda, (size_t)batch * 6 * N, &p.Lambda));
     SRI_TRY(st.out(info, (size_t)batch, &p.info));
-    // register-resident rolled Gauss-Jordan, ONE operator row per lane, one rod per CTA of 1-3 warps (measured per N against
-    // the two-rows-per-lane single-warp kernel, which stays the default for 12 <= N <= 16)
+    // N = 17 and 23 <= N <= 33 (where it is measured faster: DESIGN 2.4), default: static-order Gauss-Jordan on the operator
+    // preconditioned by the cached D_TT^-1 (one row per lane, one rod per CTA of 2-3 warps), growth-checked; the rods it hands
+    // back are re-solved with partial pivoting by the second pass
+    const bool two_pass = h->wrench_impl == 0 && (N == 17 || (N >= 23 && N <= 33));
+    if (two_pass) {
+        if (batch > 0x7fffffffLL) return fail(SRI_ERR_INVALID_ARGUMENT, "batch too large for one call (2^31 rods)");
+        SRI_TRY(list_reserve(h, 4, batch));
+        p.S = h->d_dtt + (size_t)M * M + M;
+        p.rod_count = h->d_list[4];
+        p.rod_list = h->d_list[4] + 4;
+        {
+            const double g = h->dmma_growth;
+            long long bits; std::memcpy(&bits, &g, sizeof bits);
+            p.growth_hi = g > 0.0 ? (int)(bits >> 32) : -1;   // (bound 0: every rod goes to the row-pivoting pass)
+        }
+        SRI_CUDA(cudaMemsetAsync(p.rod_count, 0, sizeof(int), h->stream));
+        h->last_handback_slot = 4;
+        if (N == 17) SRI_TRY((launch_wrench_gjs<2, 48, 6>(h, p, batch)));
+        else SRI_TRY((launch_wrench_gjs<3, 96, 1>(h, p, batch)));
+        g_launches.fetch_add(1);
+        SRI_CUDA(cudaGetLastError());
+        p.from_list = 1;   // second pass: CTAs without work exit at once
+    }
+    // row-pivoting kernels: register-resident rolled Gauss-Jordan, one row per lane over 1-3 warps, or (12 <= N <= 16, where it
+    // is faster) two rows per lane in one warp
     if ((h->wrench_impl == 0 || h->wrench_impl == 3) && N <= 11) {
         SRI_TRY((launch_wrench_gjm<1, 32, 16>(h, p, batch)));
     } else if ((h->wrench_impl == 3 && N <= 17) || (h->wrench_impl == 0 && N == 17)) {
@@ -2014,9 +2054,10 @@ int sri_get_handback_count(sri_handle h, int64_t* count) {
     SRI_ENTER(h);
     if (!count) return fail(SRI_ERR_INVALID_ARGUMENT, "sri_get_handback_count: null argument");
     *count = 0;
-    if (!h->use_dmma || !h->d_list[3]) return SRI_OK;
+    const int slot = h->last_handback_slot;
+    if ((slot == 3 && !h->use_dmma) || !h->d_list[slot]) return SRI_OK;
     int c = 0;
-    SRI_CUDA(cudaMemcpyAsync(&c, h->d_list[3], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SRI_CUDA(cudaMemcpyAsync(&c, h->d_list[slot], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     SRI_CUDA(cudaStreamSynchronize(h->stream));
     *count = c;
     return SRI_OK;

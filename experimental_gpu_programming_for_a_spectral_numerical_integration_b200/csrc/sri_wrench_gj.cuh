@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(32 * kWrenchGjWarps, 2) wrench_local_solve_gj_
     const int i0 = r0 / 3, c0 = r0 - 3 * i0, i1 = r1 / 3, c1 = r1 - 3 * i1;
 
     const long long warps_total = (long long)gridDim.x * kWrenchGjWarps;
-    for (long long rod = (long long)blockIdx.x * kWrenchGjWarps + warp; rod < p.batch; rod += warps_total) {
+    const long long count = p.from_list ? (long long)*p.rod_count : p.batch;
+    for (long long it = (long long)blockIdx.x * kWrenchGjWarps + warp; it < count; it += warps_total) {
+        const long long rod = p.from_list ? (long long)p.rod_list[it] : it;
         // ---- this rod's curvature samples, rotations by node -----------------------------------------------------------------
         for (int e = lane; e < 48; e += 32) { const int c = e >> 4, i = e & 15; kk[e] = i < N ? p.K[rod * 3 * N + c * N + i] : 0.0; }
         if (lane < 16) {

@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) wrench_local_solve_gj_multi_ker
     const bool real = row < n;
     for (int i = tid; i < C::NODES; i += 32 * NW) dti[i] = i < M ? p.D_TI[i] : 0.0;
 
-    for (long long rod = blockIdx.x; rod < p.batch; rod += gridDim.x) {
+    const long long count = p.from_list ? (long long)*p.rod_count : p.batch;
+    for (long long it = blockIdx.x; it < count; it += gridDim.x) {
+        const long long rod = p.from_list ? (long long)p.rod_list[it] : it;
         __syncthreads();
         for (int e = tid; e < 3 * C::NODES; e += 32 * NW) { const int c = e / C::NODES, i = e - c * C::NODES; kk[e] = i < N ? p.K[rod * 3 * N + c * N + i] : 0.0; }
         if (tid <= M) {

@@ -51,6 +51,12 @@ struct WrenchParams {
     const double *K, *Q, *q0, *Gamma, *fbar, *lbar, *F_tip, *M_tip;
     double* Lambda;      // [batch][6][N]
     int* info;
+    // static-order first pass + row-pivoting second pass (sri_wrench_gj_static.cuh); all null / zero otherwise
+    const double* S;     // [M][M] D_TT^-1, column-major
+    int* rod_count;      // hand-back list: number of rods, then (rod_list) their indices
+    int* rod_list;
+    int growth_hi;       // bound on |multiplier| as the high word of the double
+    int from_list;       // 1: this launch processes the rods of the list instead of 0..batch-1
 };
 
 __device__ __forceinline__ void quat_to_rot_rm(const quat& q, double* R) {  // Eigen toRotationMatrix, row-major

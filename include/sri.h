@@ -299,8 +299,9 @@ int64_t sri_kernel_launch_count(void);
 /* N <= 16: the elimination runs on the FP64 tensor cores in static pivot order; a rod whose sub-diagonal growth
  * max_{i>k} |c_ik| / |c_kk| exceeds the accepted bound (4; environment SRI_DMMA_GROWTH at sri_create) is handed
  * back to the row-pivoting kernel inside the same call; 17 <= N <= 64 works the same way with the multi-warp DMMA
- * kernel.  Returns how many rods of the most recent device-buffer call on this handle took that second pass
- * (synchronises the handle's stream); 0 when the handle runs the row-pivoting kernels only (SRI_FUSED16_IMPL=scalar). */
+ * kernel.  sri_integrate_wrench_local (N <= 33) has the same two passes with scalar kernels.  Returns how many rods of the
+ * most recent such device-buffer call on this handle took the second pass (synchronises the handle's stream); 0 when the
+ * handle runs the row-pivoting kernels only (SRI_FUSED16_IMPL=scalar; SRI_WRENCH_IMPL set). */
 int sri_get_handback_count(sri_handle h, int64_t* count);
 /* Runs the library's FP64 FMA peak probe on the handle's device and returns TFLOP/s (roofline denominator). */
 int sri_measure_fp64_peak(sri_handle h, double* tflops);

@@ -20,8 +20,9 @@ def timeit(fn, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 ms = timeit(lambda: h.integrate_wrench_local(K, out["Q"], F, Mt, fbar=fb, out=lam))
+hb = h.handback_count()
 n3 = 3 * (N - 1)
-print(json.dumps({"op": f"sri_integrate_wrench_local ({n3}x{n3} LU + 2 solves per rod)", "N": N, "rods": B, "ms": ms, "rods_per_s": B / ms * 1e3,
+print(json.dumps({"op": f"sri_integrate_wrench_local ({n3}x{n3} LU + 2 solves per rod)", "N": N, "rods": B, "ms": ms, "rods_per_s": B / ms * 1e3, "handed_back": hb,
                   "gflops_lu": B / ms * 1e3 * (2 * n3 ** 3 / 3 + 4 * n3 ** 2) * 1e-9}))
 ms = timeit(lambda: h.wrench_local(out["Q"], out["n"], out["m"], F, Mt, out=lam))
 print(json.dumps({"op": "sri_wrench_local (pointwise)", "N": N, "rods": B, "ms": ms, "rods_per_s": B / ms * 1e3}))
