@@ -111,6 +111,12 @@ struct sri_context {
         sri::NewtonState* state = nullptr;       // device: convergence flag, singular count, norm history
         sri::NewtonState* host_state = nullptr;  // two pinned mirrors: test t is copied to mirror t & 1 (followed by event t & 1)
         cudaEvent_t ev[2] = {nullptr, nullptr};
+        // one Newton iteration + its device-side convergence test as a CUDA graph (lagged mode), replayed from iteration 2 on
+        struct GraphKey { double H[3], tol, dof, fd_step; const void* block; void* comm; cudaStream_t stream; };  // (no padding: compared bytewise)
+        cudaGraphExec_t graph = nullptr;
+        GraphKey graph_key{};
+        long long graph_kernels = 0;     // kernel nodes per replay (for sri_kernel_launch_count)
+        bool graph_off = false;          // SRI_NEWTON_GRAPH=0, or a capture failed on this handle
     } newton;
     double* d_partial = nullptr;  // block partials of galerkin_residual_kernel's norms, and its ticket counter
     size_t partial_cap = 0;
@@ -912,6 +918,7 @@ int sri_destroy(sri_handle h) {
     if (h->d_jac) cudaFree(h->d_jac);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_counter) cudaFree(h->d_counter);
+    if (h->newton.graph) cudaGraphExecDestroy(h->newton.graph);
     if (h->newton.block) cudaFree(h->newton.block);
     for (int sl = 0; sl < 5; ++sl)
         if (h->d_list[sl]) cudaFree(h->d_list[sl]);
@@ -1669,7 +1676,9 @@ int sri_nccl_allreduce_norms(sri_handle h, double* norm2_and_max) {
 // (or copied, single rank), newton_check_kernel turns them into a device-side `done` flag, and the host enqueues
 // iteration k+1 BEFORE it waits for the 16 bytes of iteration k (pinned mirror + event): the test lags by one iteration
 // and the GPU never idles on the host.  Kernels enqueued after convergence see the flag and exit, so qe, the iteration
-// count and the history are exactly those of the unlagged loop.
+// count and the history are exactly those of the unlagged loop.  From the second iteration on, one iteration + its test
+// (8-12 stream operations) is ONE CUDA graph launch, captured once per workspace / H / tol (SRI_NEWTON_GRAPH=0 keeps eager
+// launches; so does a communicator of more than one rank, see below): worth 1 % at 10^5 rods and 5-8 % at 3 000-12 500.
 // reduce != NULL: the caller's host callback reduces the norms; the loop synchronises once per iteration.
 int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H_diag, const double* F_tip,
                             const double* M_tip, const double* K0, double* qe, double tol, int max_iter, double fd_step,
@@ -1688,6 +1697,7 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
     auto& ws = h->newton;
     if (ws.B != B || ws.ne != ne || ws.has_K0 != (K0 != nullptr) || ws.analytic != analytic || !ws.block) {
         SRI_CUDA(cudaStreamSynchronize(h->stream));
+        if (ws.graph) { cudaGraphExecDestroy(ws.graph); ws.graph = nullptr; }
         if (ws.block) SRI_CUDA(cudaFree(ws.block));
         ws.block = nullptr; ws.B = -1;
         const bool k0 = K0 != nullptr;
@@ -1709,9 +1719,26 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         ws.sinfo = reinterpret_cast<int*>(ws.block + off);
         ws.B = B; ws.ne = ne; ws.has_K0 = k0; ws.analytic = analytic;
     }
-    if (!ws.host_state) SRI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ws.host_state), 2 * sizeof(NewtonState)));
+    if (!ws.host_state) {
+        SRI_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ws.host_state), 2 * sizeof(NewtonState)));
+        if (const char* g = std::getenv("SRI_NEWTON_GRAPH")) ws.graph_off = std::atoi(g) == 0;
+    }
     for (cudaEvent_t& e : ws.ev)
         if (!e) SRI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // The legacy default stream cannot be captured.  This call is synchronous for the host anyway (it returns after qe has
+    // been copied back), so in that case the loop runs on the handle's own stream, ordered after the work already queued on
+    // the caller's stream, and the handle's stream is restored on the way out.
+    struct StreamSwap { sri_context* h; cudaStream_t saved; bool on = false; ~StreamSwap() { if (on) h->stream = saved; } } swap{h, h->stream};
+    // (Several ranks: the iteration is NOT captured.  An ncclAllGather recorded into the graph on two ranks hung in this
+    // build's test run; with a communicator of more than one rank the loop keeps the eager launches it was verified with.)
+    const bool use_graph = lagged && !ws.graph_off && !(h->nccl_comm && h->nccl_nranks > 1);
+    if (use_graph && (h->stream == nullptr || h->stream == cudaStreamLegacy) && h->own_stream) {
+        if (!h->pipe_event) SRI_CUDA(cudaEventCreateWithFlags(&h->pipe_event, cudaEventDisableTiming));
+        SRI_CUDA(cudaEventRecord(h->pipe_event, h->stream));
+        SRI_CUDA(cudaStreamWaitEvent(h->own_stream, h->pipe_event, 0));
+        h->stream = h->own_stream;
+        swap.on = true;
+    }
     cudaStream_t st = h->stream;
     SRI_CUDA(cudaMemsetAsync(ws.state, 0, sizeof(NewtonState), st));
     SRI_CUDA(cudaMemsetAsync(ws.red, 0, 2 * sizeof(double), st));  // a rank without rods contributes (0, 0)
@@ -1761,13 +1788,65 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
     const double dof = (double)(total_dof > 0 ? total_dof : (int64_t)n * B);
     const int nranks = std::max(1, h->nccl_nranks);
     // device-side convergence test number `t` and the asynchronous copy of its outcome to the pinned mirror
-    auto test = [&](int t) -> int {
+    auto test_device = [&]() -> int {
         SRI_TRY(gather_norms(h, ws.red));
         newton_check_kernel<<<1, 32, 0, st>>>(h->d_gather, nranks, dof, tol, ws.state);
         g_launches.fetch_add(1);
         SRI_CUDA(cudaGetLastError());
+        return SRI_OK;
+    };
+    auto test_mirror = [&](int t) -> int {
         SRI_CUDA(cudaMemcpyAsync(ws.host_state + (t & 1), ws.state, sizeof(NewtonState), cudaMemcpyDeviceToHost, st));
         SRI_CUDA(cudaEventRecord(ws.ev[t & 1], st));
+        return SRI_OK;
+    };
+    auto test = [&](int t) -> int {
+        SRI_TRY(test_device());
+        return test_mirror(t);
+    };
+    // iterate() + test_device() as one graph launch.  Every argument of every node is fixed for the lifetime of the workspace
+    // (pointers into ws.block, handle tables) or part of the key below; the first iteration of a call always runs eagerly, so
+    // every lazy allocation and attribute of the kernels involved exists before a capture starts.
+    auto iterate_and_test_graph = [&]() -> int {
+        sri_context::NewtonWorkspace::GraphKey key{};
+        key.H[0] = H[0]; key.H[1] = H[1]; key.H[2] = H[2]; key.tol = tol; key.dof = dof; key.fd_step = fd_step;
+        key.block = ws.block; key.comm = h->nccl_comm; key.stream = st;
+        if (ws.graph && std::memcmp(&key, &ws.graph_key, sizeof key) != 0) { cudaGraphExecDestroy(ws.graph); ws.graph = nullptr; }
+        if (!ws.graph) {
+            const long long before = g_launches.load();
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {   // (a stream that cannot be captured)
+                cudaGetLastError();
+                ws.graph_off = true;
+                SRI_TRY(iterate());
+                return test_device();
+            }
+            int rc = iterate();
+            if (rc == SRI_OK) rc = test_device();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            const long long captured = g_launches.load() - before;
+            g_launches.fetch_sub(captured);   // (recorded, not run)
+            if (rc != SRI_OK || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                ws.graph_off = true;   // this handle falls back to eager launches
+                if (rc != SRI_OK) return rc;
+                SRI_TRY(iterate());
+                return test_device();
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&ws.graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) {
+                cudaGetLastError();
+                ws.graph = nullptr; ws.graph_off = true;
+                SRI_TRY(iterate());
+                return test_device();
+            }
+            ws.graph_key = key;
+            ws.graph_kernels = captured;
+        }
+        SRI_CUDA(cudaGraphLaunch(ws.graph, st));
+        g_launches.fetch_add(ws.graph_kernels);
         return SRI_OK;
     };
 
@@ -1781,8 +1860,13 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
         for (int it = 0;; ++it) {
             // enqueue iteration it+1 and its test before looking at test `it` (no-ops on the device if `it` converged)
             if (it < max_iter) {
-                SRI_TRY(iterate());
-                SRI_TRY(test(it + 1));
+                if (it >= 1 && B > 0 && use_graph && !ws.graph_off) {
+                    SRI_TRY(iterate_and_test_graph());
+                    SRI_TRY(test_mirror(it + 1));
+                } else {
+                    SRI_TRY(iterate());
+                    SRI_TRY(test(it + 1));
+                }
                 last_mirror = (it + 1) & 1;
             }
             // test `it` was copied to mirror it & 1; the next copy into that mirror (test it + 2) is only enqueued in the next

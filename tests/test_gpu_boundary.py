@@ -291,6 +291,39 @@ def test_lagged_device_side_convergence_test_takes_the_same_steps(h16, torch_mod
     assert torch_mod.equal(q_a, q_b)
 
 
+@pytest.mark.parametrize("fd_step", [0.0, 1e-6])
+def test_newton_iteration_as_cuda_graph_replays_the_eager_loop(sri_lib, torch_mod, fd_step, monkeypatch):
+    """From its second iteration on the lagged loop launches one CUDA graph per iteration (captured once per workspace, H,
+    tolerance).  Same iterates, history and kernel count as eager launches (SRI_NEWTON_GRAPH=0); a changed H or tolerance
+    re-captures instead of replaying stale arguments."""
+    from experimental_gpu_programming_for_a_spectral_numerical_integration_b200 import SpectralRodIntegrator, kernel_launch_count
+    B, ne = 1500, 3
+    rng = np.random.default_rng(77)
+    F = np.zeros((B, 3)); F[:, 2] = -rng.uniform(0.1, 2.0, size=B)
+    Mt = rng.uniform(-0.1, 0.1, size=(B, 3))
+    tF, tM = (torch_mod.from_numpy(a).cuda() for a in (F, Mt))
+    cases = [((1.0, 1.0, 0.77), 1e-10), ((1.0, 1.0, 0.77), 1e-10), ((2.0, 1.5, 0.9), 1e-10), ((2.0, 1.5, 0.9), 1e-6)]
+
+    def run_all():
+        out = []
+        with SpectralRodIntegrator(16, 0) as h:
+            for H, tol in cases:
+                n0 = kernel_launch_count()
+                q, rep = h.newton_static_shape(tF, tM, ne, H, fd_step=fd_step, tol=tol)
+                out.append((q.cpu().numpy(), rep, kernel_launch_count() - n0))
+        return out
+
+    graph = run_all()
+    monkeypatch.setenv("SRI_NEWTON_GRAPH", "0")
+    eager = run_all()
+    for (qg, rg, ng), (qe_, re_, ne_) in zip(graph, eager):
+        assert rg["converged"] and rg["iterations"] >= 3
+        assert rg["rms_history"] == re_["rms_history"] and rg["iterations"] == re_["iterations"]
+        assert np.array_equal(qg, qe_)
+        assert ng == ne_
+    assert graph[3][1]["iterations"] < graph[2][1]["iterations"]   # the looser tolerance was honoured, not the captured one
+
+
 def test_singular_newton_systems_are_counted_and_skipped(h16, torch_mod):
     """H = 0 and no load: residual and Jacobian vanish identically, every per-rod system is singular; the update must be
     skipped (qe stays finite) and the report must say so (NaN used to be written silently)."""
