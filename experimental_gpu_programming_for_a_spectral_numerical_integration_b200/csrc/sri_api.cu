@@ -112,7 +112,7 @@ struct sri_context {
         sri::NewtonState* host_state = nullptr;  // two pinned mirrors: test t is copied to mirror t & 1 (followed by event t & 1)
         cudaEvent_t ev[2] = {nullptr, nullptr};
         // one Newton iteration + its device-side convergence test as a CUDA graph (lagged mode), replayed from iteration 2 on
-        struct GraphKey { double H[3], tol, dof, fd_step; const void* block; void* comm; cudaStream_t stream; };  // (no padding: compared bytewise)
+        struct GraphKey { double H[3], tol, dof, fd_step; const void* block; const void* list; void* comm; cudaStream_t stream; };  // (no padding: compared bytewise)
         cudaGraphExec_t graph = nullptr;
         GraphKey graph_key{};
         long long graph_kernels = 0;     // kernel nodes per replay (for sri_kernel_launch_count)
@@ -1810,7 +1810,7 @@ int sri_newton_static_shape(sri_handle h, int64_t batch, int ne, const double* H
     auto iterate_and_test_graph = [&]() -> int {
         sri_context::NewtonWorkspace::GraphKey key{};
         key.H[0] = H[0]; key.H[1] = H[1]; key.H[2] = H[2]; key.tol = tol; key.dof = dof; key.fd_step = fd_step;
-        key.block = ws.block; key.comm = h->nccl_comm; key.stream = st;
+        key.block = ws.block; key.list = h->d_list[3]; key.comm = h->nccl_comm; key.stream = st;   // (the hand-back list may be re-allocated by a larger call in between)
         if (ws.graph && std::memcmp(&key, &ws.graph_key, sizeof key) != 0) { cudaGraphExecDestroy(ws.graph); ws.graph = nullptr; }
         if (!ws.graph) {
             const long long before = g_launches.load();
