@@ -237,7 +237,11 @@ int sri_shape_jacobian(sri_handle h, int64_t batch, int ne, const double* H_diag
  * ncclAllGather of 16 bytes per iteration on the handle's stream) or, without one, over this handle's rods only.  In that
  * mode the convergence test is a kernel that sets a device-side flag, the host enqueues iteration k+1 before it reads the
  * norms of iteration k (the test lags by one iteration, so the GPU never waits for the host), and every
- * kernel of an iteration enqueued after convergence exits at once: iterates and counts are those of the unlagged loop. */
+ * kernel of an iteration enqueued after convergence exits at once: iterates and counts are those of the unlagged loop.
+ * On a single rank one iteration + its test is replayed as ONE CUDA graph launch from the second iteration on (captured
+ * once per problem shape / H / tol; environment SRI_NEWTON_GRAPH=0 keeps eager launches, a communicator of more than one
+ * rank does too).  A handle whose stream is the legacy default stream (which cannot be captured) runs this call on its own
+ * stream, ordered after the work already queued on the caller's; the call returns after qe has been copied back either way. */
 typedef int (*sri_allreduce_fn)(double* norm2_and_max, void* ctx);
 typedef struct sri_newton_report {
     int iterations;        /* Newton updates taken */
